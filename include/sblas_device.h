@@ -1,0 +1,75 @@
+/* sblas_device.h -- the boundary between the C host code and the sm_100a kernels.
+ * Plain C: a POD argument block per work unit and extern "C" launchers that take
+ * device pointers and a stream.  No torch types, no C++ in the signatures.
+ *
+ * A "segment" is one unit of work of the reference path: a v1 shard
+ * (spmv/src/dspmv_mgpu_v1.cu:59-133), a v2 task (dspmv_mgpu_v2.cu:211-289) or a
+ * baseline row block (dspmv_mgpu_baseline.cu:60-87): a contiguous nnz range
+ * [nz0, nz1) of the arrays resident on one GPU plus the rows it touches.  The
+ * launch replaces the per-GPU / per-task cusparseDcsrmv[_mp] call
+ * (dspmv_mgpu_baseline.cu:163, dspmv_mgpu_v1.cu:200,206, dspmv_mgpu_v2.cu:351,357).
+ */
+#ifndef SBLAS_DEVICE_H
+#define SBLAS_DEVICE_H
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sblas_seg_args {
+    const double *val;    /* values of this GPU's resident nnz range                      */
+    const int *col;       /* column indices, same range                                   */
+    const int *rowptr;    /* int32 row pointer, rebased to the GPU's range and clamped     */
+    const double *x;      /* full x (replicated on every GPU)                              */
+    double *y;            /* this GPU's y slice (index 0 == the GPU's first row)           */
+    double *edge;         /* [2] raw partial sums of a split first / last row              */
+    double *carry;        /* [ntile] tile kernel: sum of the row left open by tile j-1     */
+    double *tail;         /* [ntile] tile kernel: partial of a row that leaves tile j      */
+    const int *tstart;    /* [ntile+1] first row that STARTS inside tile j                 */
+    double alpha, beta;
+    int row_lo, row_hi;   /* rows of the segment, inclusive, GPU-local numbering           */
+    int nz0, nz1;         /* nnz range [nz0, nz1), GPU-local numbering                     */
+    int skip_first;       /* row whose raw sum goes to edge[0] instead of y (or -1)        */
+    int skip_last;        /* row whose raw sum goes to edge[1] instead of y (or -1)        */
+    int tile0;            /* absolute index of the segment's first tile (nz0 / tile)       */
+    int ntile;
+} sblas_seg_args;
+
+/* kernel families (the `kernel` argument of the reference API maps onto these,
+ * see sblas_plan.c) */
+enum { SBLAS_K_VECTOR = 1, SBLAS_K_TILE = 2 };
+
+/* nnz per tile of the tile kernel for a given items-per-thread choice */
+int sblas_tile_size(int ipt);
+
+/* int64 harness row pointer slice -> int32 GPU-local row pointer:
+ * out[i] = clamp(rp64[i] - first_idx, 0, total_nnz), i in [0,count).  Reproduces
+ * the local row pointer of dspmv_mgpu_v1.cu:125-133 / dspmv_mgpu_baseline.cu:82-85. */
+cudaError_t sblas_launch_rebase_rowptr(const long long *rp64, long long first_idx, int total_nnz,
+                                       long long count, int *out, cudaStream_t s);
+
+/* tstart[j] for j in [0,ntile]: first row whose first entry lies at or after the
+ * start of tile j (binary search per tile; replaces CSR5's tile pointer
+ * generation, spmv/include/detail/cuda/format_cuda.h:21-42). */
+cudaError_t sblas_launch_tile_rows(const sblas_seg_args *a, int tile, int *tstart_out, cudaStream_t s);
+
+/* y[row_lo..row_hi] = alpha*A_seg*x + beta*y for one segment. kind: SBLAS_K_*;
+ * ipt: items per thread of the tile kernel (4, 8 or 16); lanes: lanes per row of
+ * the vector kernel (0 = choose from the mean row length). */
+cudaError_t sblas_launch_spmv_segment(const sblas_seg_args *a, int kind, int ipt, int lanes, cudaStream_t s);
+
+/* finish rows split between segments: y[mrow[i]] = alpha * sum_k *msrc[k] + beta*y[..],
+ * k in [mbeg[i], mbeg[i+1]) in list order (ascending segment order).  Sources may be
+ * peer-GPU addresses (NVLink P2P).  Replaces the host merges of
+ * dspmv_mgpu_v1.cu:235-248 and dspmv_mgpu_v2.cu:385-441. */
+cudaError_t sblas_launch_edge_merge(const int *mrow, const int *mbeg, const double *const *msrc, int nmerge,
+                                    double *y, double alpha, double beta, cudaStream_t s);
+
+/* device fill helpers used by the plan */
+cudaError_t sblas_launch_fill_f64(double *p, long long n, double v, cudaStream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,158 @@
+/*
+ * sblas_spmv.h -- C-ABI of the B200-native multi-GPU CSR SpMV library
+ * (libsblas_spmv.so).  y = alpha*A*x + beta*y, double precision, CSR with the
+ * harness's 64-bit row pointer.
+ *
+ * This is the drop-in boundary for ONE path of pnnl/s-blas: the three host entry
+ * points of spmv/include/spmv_kernel.h:11-36 and what they call.  Every symbol is
+ * extern "C", takes plain pointers and sizes, and cites the reference interface it
+ * replaces.  The same three functions are additionally exported under the
+ * reference's own names (C linkage for C callers, and the reference's C++-mangled
+ * names for an unmodified spmv/test/dspmv_test.cu) by include/spmv_kernel.h.
+ *
+ * Return convention (spmv/src/dspmv_mgpu_baseline.cu:77-79,99-153,173-175;
+ * dspmv_mgpu_v1.cu:114-116,141-157,226-228; dspmv_mgpu_v2.cu:44-46):
+ *    0  success
+ *   -1  shard larger than 0.8 x the smallest free device memory, kernel failure,
+ *       or (v2) nb <= 0 || ngpu == 0 || q == 0
+ *    1  set-up failure (device, stream, allocation, copy)
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef SBLAS_SPMV_H
+#define SBLAS_SPMV_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ one-shot API
+ * Host pointers in, host y out; replaces, argument for argument,
+ *   spMV_mgpu_baseline  spmv/include/spmv_kernel.h:11-15  (spmv/src/dspmv_mgpu_baseline.cu:14)
+ *   spMV_mgpu_v1        spmv/include/spmv_kernel.h:16-21  (spmv/src/dspmv_mgpu_v1.cu:16)
+ *   spMV_mgpu_v2        spmv/include/spmv_kernel.h:23-30  (spmv/src/dspmv_mgpu_v2.cu:33)
+ * kernel: 1 = adaptive (binned per tile), 2 = nnz-balanced tile kernel everywhere,
+ *         3 = CSR5-style small tiles (the reference's kernel 3 is a no-op).
+ */
+int sblas_spmv_mgpu_baseline(int m, int n, long long nnz, double *alpha, double *csrVal,
+                             long long *csrRowPtr, int *csrColIndex, double *x, double *beta,
+                             double *y, int ngpu);
+int sblas_spmv_mgpu_v1(int m, int n, long long nnz, double *alpha, double *csrVal,
+                       long long *csrRowPtr, int *csrColIndex, double *x, double *beta,
+                       double *y, int ngpu, int kernel);
+int sblas_spmv_mgpu_v2(int m, int n, long long nnz, double *alpha, double *csrVal,
+                       long long *csrRowPtr, int *csrColIndex, double *x, double *beta,
+                       double *y, int ngpu, int kernel, long long nb, int copy_of_workspace);
+
+/* helpers of spmv/include/spmv_kernel.h:32-36 (spmv/src/spmv_helper.cu:16-39,41-48,51-76) */
+int sblas_get_row_from_index(int n, const long long *a, long long idx);
+double sblas_get_time(void);
+double sblas_get_gpu_availble_mem(int ngpu);
+
+/* ------------------------------------------------------------------ partitioners
+ * Host-side, pure integer work; bit-exact restatements of the reference formulas.
+ * One record per GPU (baseline, v1) or per task (v2); field names follow
+ * struct spmv_task (spmv/include/spmv_task.h:4-36). */
+typedef struct sblas_part {
+    long long start_idx, end_idx;   /* inclusive nnz range                       */
+    int start_row, end_row;         /* rows containing start_idx / end_idx       */
+    int start_flag, end_flag;       /* 1 = the row is shared with a neighbour    */
+    int dev_m, dev_nnz;
+} sblas_part;
+
+/* spmv/src/dspmv_mgpu_baseline.cu:60-87 (flags are always 0) */
+int sblas_partition_baseline(int m, const long long *csrRowPtr, int ngpu, sblas_part *out);
+/* spmv/src/dspmv_mgpu_v1.cu:59-100,119 */
+int sblas_partition_v1(int m, long long nnz, const long long *csrRowPtr, int ngpu, sblas_part *out);
+/* spmv/src/dspmv_mgpu_v2.cu:218 (task count) and :211-275 (generate_tasks) */
+int sblas_v2_num_tasks(long long nnz, long long nb);
+int sblas_generate_tasks_v2(int m, long long nnz, const long long *csrRowPtr, long long nb, sblas_part *out);
+/* task -> GPU map: GPU d owns tasks [T*d/ngpu, T*(d+1)/ngpu): the quota of
+ * dspmv_mgpu_v2.cu:125-126 with a fixed (deterministic) assignment */
+int sblas_v2_task_owner(int T, int ngpu, int task);
+/* local int32 row pointer of one shard/task: dspmv_mgpu_v1.cu:125-133 and
+ * dspmv_mgpu_v2.cu:279-289 (baseline != 0: dspmv_mgpu_baseline.cu:82-85).
+ * out has dev_m + 1 entries. */
+void sblas_local_rowptr(const long long *csrRowPtr, const sblas_part *p, int baseline, int *out);
+
+/* ------------------------------------------------------------------ plan API
+ * The reference re-uploads the matrix on every call.  A plan keeps
+ * the partition, the device-resident shards, the int32 row pointers and the tile
+ * metadata, so that repeated products touch only HBM (and NVLink for the
+ * boundary rows).  The one-shot functions above are create + execute + destroy.
+ */
+typedef struct sblas_spmv_plan sblas_spmv_plan;
+
+enum { SBLAS_BASELINE = 0, SBLAS_V1 = 1, SBLAS_V2 = 2 };
+
+/* In-process multi-GPU plan on devices 0..ngpu-1 from HOST arrays (pinned or
+ * pageable).  version: SBLAS_*.  nb / q are only used by SBLAS_V2. */
+int sblas_spmv_plan_create(sblas_spmv_plan **plan, int version, int m, int n, long long nnz,
+                           const double *csrVal, const long long *csrRowPtr, const int *csrColIndex,
+                           int ngpu, int kernel, long long nb, int q);
+
+/* One-process-per-GPU plan: this process holds only shard `rank` of `world`
+ * (same partition formulas) on CUDA device `device`.  The CSR arrays are HOST
+ * pointers to the WHOLE matrix unless SBLAS_SRC_DEVICE_SHARD is set in `flags`,
+ * in which case csrVal/csrColIndex are DEVICE pointers to exactly this rank's
+ * nnz range [start_idx, end_idx] (adopted, not copied) and csrRowPtr is still
+ * the whole host row pointer. */
+enum { SBLAS_SRC_HOST = 0, SBLAS_SRC_DEVICE_SHARD = 1 };
+int sblas_spmv_plan_create_rank(sblas_spmv_plan **plan, int version, int m, int n, long long nnz,
+                                const double *csrVal, const long long *csrRowPtr, const int *csrColIndex,
+                                int world, int rank, int device, int kernel, long long nb, int q, int flags);
+
+/* y = alpha*A*x + beta*y with HOST x (length n) and HOST y (length m, in/out):
+ * uploads x (and y when beta != 0), runs every segment, downloads y and merges
+ * the split boundary rows in ascending segment order. In a rank plan only this
+ * rank's rows of y are written; rows shared with other ranks are left to
+ * sblas_spmv_plan_edges / the caller's exchange. */
+int sblas_spmv_plan_execute(sblas_spmv_plan *plan, const double *alpha, const double *x,
+                            const double *beta, double *y);
+
+/* Device-resident execute: x and y already sit in the plan's device buffers
+ * (see sblas_spmv_plan_x / _y); nothing crosses PCIe.  Enqueues on the plan's
+ * streams and returns without synchronising unless sync != 0. */
+int sblas_spmv_plan_execute_device(sblas_spmv_plan *plan, double alpha, double beta, int sync);
+
+/* accessors (dev = index of the GPU inside the plan, 0 for a rank plan) */
+int sblas_spmv_plan_num_devices(const sblas_spmv_plan *plan);
+int sblas_spmv_plan_num_segments(const sblas_spmv_plan *plan);
+int sblas_spmv_plan_segment(const sblas_spmv_plan *plan, int seg, sblas_part *out, int *device);
+double *sblas_spmv_plan_x(sblas_spmv_plan *plan, int dev);            /* device pointer, n doubles      */
+double *sblas_spmv_plan_y(sblas_spmv_plan *plan, int dev, int *first_row, int *rows); /* device y slice */
+const int *sblas_spmv_plan_rowptr(sblas_spmv_plan *plan, int dev, int *count);        /* device int32   */
+void *sblas_spmv_plan_stream(sblas_spmv_plan *plan, int dev);         /* cudaStream_t of the GPU        */
+/* raw partial sums of split rows after an execute: out[2*seg] (first row) and
+ * out[2*seg+1] (last row); valid where the segment's start_flag / end_flag is set */
+int sblas_spmv_plan_edges(sblas_spmv_plan *plan, double *out);
+/* device pointer of the edge table of one GPU (2 doubles per local segment) */
+double *sblas_spmv_plan_edge_ptr(sblas_spmv_plan *plan, int dev);
+/* Rank plans: number of doubles each rank contributes to the exchange of split-row
+ * partials (2 per local segment, padded to the largest rank), and the merge that
+ * finishes the rows this rank owns from a table holding every rank's block
+ * (world x edge_slots doubles, rank-major: the output of an all-gather of each
+ * rank's sblas_spmv_plan_edge_ptr block, or a peer-mapped symmetric buffer).
+ * Enqueued on the plan's stream; ascending segment order (deterministic). */
+int sblas_spmv_plan_edge_slots(const sblas_spmv_plan *plan);
+int sblas_spmv_plan_merge_gathered(sblas_spmv_plan *plan, const double *gathered, double alpha, double beta);
+/* Rank plans: make the local segments write their edge partials into caller-owned
+ * device memory (edge_slots doubles), e.g. a torch tensor that is all-gathered or a
+ * symmetric-memory buffer peers can read over NVLink. */
+int sblas_spmv_plan_bind_edge_table(sblas_spmv_plan *plan, double *device_block);
+/* blocking copy helper for callers without a CUDA binding of their own
+ * (kind: 1 host->device, 2 device->host, 3 device->device); returns the cudaError_t */
+int sblas_memcpy(void *dst, const void *src, unsigned long long bytes, int kind);
+int sblas_device_synchronize(void);
+/* algorithmic bytes of one execute: 12*nnz + 4*(rows+1)
+ * + 8*x_touched + 8*rows*(1 + [beta != 0]), summed over the plan's GPUs */
+double sblas_spmv_plan_alg_bytes(const sblas_spmv_plan *plan, int beta_nonzero, long long x_touched_per_gpu);
+/* number of kernel launches one execute enqueues (all GPUs of the plan) */
+int sblas_spmv_plan_launches(const sblas_spmv_plan *plan);
+void sblas_spmv_plan_destroy(sblas_spmv_plan *plan);
+
+const char *sblas_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBLAS_SPMV_H */

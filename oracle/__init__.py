@@ -1,0 +1,216 @@
+"""oracle -- TEST INFRASTRUCTURE ONLY (the checker, never the product).
+
+ctypes front-end of oracle/spmv_oracle.c (the CPU restatement of the s-BLAS
+multi-GPU CSR SpMV path; see that file's header for the parity status and the
+reference file:line each function follows) and of oracle/_ref/libref_helper.so
+(the reference's own spmv/src/spmv_helper.cu compiled where it lies by
+oracle/Makefile).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this package.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LL = C.c_longlong
+_pd = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_pi = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_pl = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+
+
+def build(force=False):
+    """Compile the checker (liboracle.so, and _ref/ when the reference checkout exists)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "spmv_oracle.c")
+    stale = force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src)
+    need_ref = os.path.exists("/root/reference/spmv/src/spmv_helper.cu") and not os.path.exists(
+        os.path.join(_HERE, "_ref", "libref_helper.so"))
+    if stale or need_ref:
+        subprocess.run(["make", "-C", _HERE, "-s"] + (["-B"] if force else []), check=True)
+    return so
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        L.oracle_csr_spmv.argtypes = [C.c_int, _pl, _pi, _pd, _pd, C.c_double, C.c_double, _pd]
+        L.oracle_csr_spmv_omp.argtypes = L.oracle_csr_spmv.argtypes
+        L.oracle_csr_spmv_omp.restype = C.c_int
+        L.oracle_csr_spmv_omp_balanced.argtypes = L.oracle_csr_spmv.argtypes
+        L.oracle_csr_spmv_omp_balanced.restype = C.c_int
+        L.oracle_csr_spmv_bound.argtypes = [C.c_int, _pl, _pi, _pd, _pd, C.c_double, C.c_double, _pd, _pd]
+        L.oracle_get_row_from_index.argtypes = [C.c_int, _pl, _LL]
+        L.oracle_get_row_from_index.restype = C.c_int
+        L.oracle_partition_baseline.argtypes = [C.c_int, _pl, C.c_int, _pi, _pi, _pi, _pi]
+        L.oracle_local_rowptr_baseline.argtypes = [_pl, C.c_int, C.c_int, _pi]
+        L.oracle_partition_v1.argtypes = [C.c_int, _LL, _pl, C.c_int, _pl, _pl, _pi, _pi, _pi, _pi, _pi, _pi]
+        L.oracle_local_rowptr_v1.argtypes = [_pl, _LL, C.c_int, C.c_int, C.c_int, _pi]
+        L.oracle_v2_num_tasks.argtypes = [_LL, _LL]
+        L.oracle_v2_num_tasks.restype = C.c_int
+        L.oracle_generate_tasks_v2.argtypes = [C.c_int, _LL, _pl, _LL, _pl, _pl, _pi, _pi, _pi, _pi, _pi, _pi]
+        L.oracle_v2_quota.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.oracle_v2_quota.restype = C.c_int
+        mg = [C.c_int, C.c_int, _LL, C.c_double, _pd, _pl, _pi, _pd, C.c_double, _pd]
+        L.oracle_spmv_mgpu_v1.argtypes = mg + [C.c_int]
+        L.oracle_spmv_mgpu_baseline.argtypes = mg + [C.c_int]
+        L.oracle_spmv_mgpu_v2.argtypes = mg + [_LL]
+        L.oracle_spmv_mgpu_v2_ex.argtypes = mg + [_LL, C.c_int]
+        L.oracle_gen_g.argtypes = [C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_gen_g.restype = _LL
+        L.oracle_srand.argtypes = [C.c_uint]
+        L.oracle_rand_unit.restype = C.c_double
+        L.oracle_coo_to_rowptr.argtypes = [C.c_int, _LL, _pi, _pl]
+        L.oracle_load_mtx.argtypes = [C.c_char_p, C.c_char, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                      C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_load_mtx.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+_ref = None
+
+
+def ref_helper():
+    """The reference's own compiled spmv_helper.cu (get_row_from_index), or None."""
+    global _ref
+    if _ref is None:
+        p = os.path.join(_HERE, "_ref", "libref_helper.so")
+        if not os.path.exists(p):
+            return None
+        R = C.CDLL(p)
+        f = getattr(R, "_Z18get_row_from_indexiPxx")     # C++ mangled, SURVEY.md F9
+        f.argtypes = [C.c_int, _pl, _LL]
+        f.restype = C.c_int
+        _ref = f
+    return _ref
+
+
+# ----------------------------------------------------------------------------- wrappers
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def csr_spmv(rowptr, col, val, x, alpha, beta, y):
+    """y_out = alpha*A*x + beta*y (oracle_csr_spmv). Returns a new array."""
+    out = _c(y, np.float64).copy()
+    lib().oracle_csr_spmv(len(rowptr) - 1, _c(rowptr, np.int64), _c(col, np.int32), _c(val, np.float64),
+                          _c(x, np.float64), alpha, beta, out)
+    return out
+
+
+def csr_spmv_bound(rowptr, col, val, x, alpha, beta, y):
+    b = np.empty(len(rowptr) - 1, np.float64)
+    lib().oracle_csr_spmv_bound(len(rowptr) - 1, _c(rowptr, np.int64), _c(col, np.int32), _c(val, np.float64),
+                                _c(x, np.float64), alpha, beta, _c(y, np.float64), b)
+    return b
+
+
+def get_row_from_index(rowptr, idx):
+    rp = _c(rowptr, np.int64)
+    return lib().oracle_get_row_from_index(len(rp) - 1, rp, int(idx))
+
+
+def partition_v1(rowptr, ngpu):
+    rp = _c(rowptr, np.int64)
+    m, nnz = len(rp) - 1, int(rp[-1])
+    si, ei = np.zeros(ngpu, np.int64), np.zeros(ngpu, np.int64)
+    a = [np.zeros(ngpu, np.int32) for _ in range(6)]
+    lib().oracle_partition_v1(m, nnz, rp, ngpu, si, ei, *a)
+    return dict(start_idx=si, end_idx=ei, start_row=a[0], end_row=a[1], start_flag=a[2], end_flag=a[3],
+                dev_m=a[4], dev_nnz=a[5])
+
+
+def partition_baseline(rowptr, ngpu):
+    rp = _c(rowptr, np.int64)
+    a = [np.zeros(ngpu, np.int32) for _ in range(4)]
+    lib().oracle_partition_baseline(len(rp) - 1, rp, ngpu, *a)
+    return dict(start_row=a[0], end_row=a[1], dev_m=a[2], dev_nnz=a[3])
+
+
+def generate_tasks_v2(rowptr, nb):
+    rp = _c(rowptr, np.int64)
+    m, nnz = len(rp) - 1, int(rp[-1])
+    T = lib().oracle_v2_num_tasks(nnz, nb)
+    si, ei = np.zeros(T, np.int64), np.zeros(T, np.int64)
+    a = [np.zeros(T, np.int32) for _ in range(6)]
+    lib().oracle_generate_tasks_v2(m, nnz, rp, nb, si, ei, *a)
+    return dict(start_idx=si, end_idx=ei, start_row=a[0], end_row=a[1], start_flag=a[2], end_flag=a[3],
+                dev_m=a[4], dev_nnz=a[5])
+
+
+def local_rowptr_v1(rowptr, start_idx, start_row, dev_m, dev_nnz):
+    out = np.zeros(dev_m + 1, np.int32)
+    lib().oracle_local_rowptr_v1(_c(rowptr, np.int64), int(start_idx), int(start_row), int(dev_m), int(dev_nnz), out)
+    return out
+
+
+def local_rowptr_baseline(rowptr, start_row, dev_m):
+    out = np.zeros(dev_m + 1, np.int32)
+    lib().oracle_local_rowptr_baseline(_c(rowptr, np.int64), int(start_row), int(dev_m), out)
+    return out
+
+
+def _mgpu(fn, rowptr, col, val, x, alpha, beta, y, *last):
+    rp = _c(rowptr, np.int64)
+    out = _c(y, np.float64).copy()
+    xx = _c(x, np.float64)
+    rc = fn(len(rp) - 1, len(xx), int(rp[-1]), alpha, _c(val, np.float64), rp,
+            _c(col, np.int32), xx, beta, out, *last)
+    assert rc == 0
+    return out
+
+
+def spmv_mgpu_v1(rowptr, col, val, x, alpha, beta, y, ngpu):
+    return _mgpu(lib().oracle_spmv_mgpu_v1, rowptr, col, val, x, alpha, beta, y, ngpu)
+
+
+def spmv_mgpu_baseline(rowptr, col, val, x, alpha, beta, y, ngpu):
+    return _mgpu(lib().oracle_spmv_mgpu_baseline, rowptr, col, val, x, alpha, beta, y, ngpu)
+
+
+def spmv_mgpu_v2(rowptr, col, val, x, alpha, beta, y, nb, faithful_y2=False):
+    """faithful_y2=True reproduces the reference's single-y2 defect (see spmv_oracle.c)."""
+    return _mgpu(lib().oracle_spmv_mgpu_v2_ex, rowptr, col, val, x, alpha, beta, y, int(nb), 1 if faithful_y2 else 0)
+
+
+def gen_g(n, r1=0.9, r2=0.01, seed=1):
+    """The harness `g` generator (glibc rand(), srand(seed); the harness never seeds => seed 1).
+    Returns (coo_row, coo_col, val, alpha, beta) with ALPHA/BETA drawn right after, as in
+    dspmv_test.cu:281-282."""
+    L = lib()
+    nnz = L.oracle_gen_g(n, r1, r2, None, None, None)
+    if nnz < 0:
+        raise ValueError("n must be a positive multiple of 8")
+    r, c, v = np.empty(nnz, np.int32), np.empty(nnz, np.int32), np.empty(nnz, np.float64)
+    L.oracle_srand(seed)
+    L.oracle_gen_g(n, r1, r2, r.ctypes.data, c.ctypes.data, v.ctypes.data)
+    alpha = L.oracle_rand_unit()
+    beta = L.oracle_rand_unit()
+    return r, c, v, alpha, beta
+
+
+def coo_to_rowptr(m, coo_row):
+    rp = np.zeros(m + 1, np.int64)
+    lib().oracle_coo_to_rowptr(m, len(coo_row), _c(coo_row, np.int32), rp)
+    return rp
+
+
+def load_mtx(path, mode="f"):
+    """The harness loader (file order kept, not row sorted, symmetric flag ignored)."""
+    L = lib()
+    m, n, nz = C.c_int(), C.c_int(), C.c_int()
+    rc = L.oracle_load_mtx(path.encode(), mode.encode(), C.byref(m), C.byref(n), C.byref(nz), None, None, None)
+    if rc:
+        raise IOError("oracle_load_mtx rc=%d" % rc)
+    r, c, v = np.zeros(nz.value, np.int32), np.zeros(nz.value, np.int32), np.zeros(nz.value, np.float64)
+    L.oracle_load_mtx(path.encode(), mode.encode(), C.byref(m), C.byref(n), C.byref(nz),
+                      r.ctypes.data, c.ctypes.data, v.ctypes.data)
+    return m.value, n.value, r, c, v

@@ -1,0 +1,367 @@
+"""s-blas_b200 -- B200-native multi-GPU CSR SpMV behind the s-BLAS API.
+
+Python mirror of the reference interface for ONE path (pnnl/s-blas
+spmv/include/spmv_kernel.h:11-36): spMV_mgpu_baseline / spMV_mgpu_v1 / spMV_mgpu_v2
+with the same names, argument meaning and return codes, plus the plan API of
+include/sblas_spmv.h.  Everything here is a ctypes call into
+s-blas_b200/lib/libsblas_spmv.so (host C + hand-written sm_100a kernels); there is
+no Python or CPU arithmetic and no fallback: if the library is missing the import
+of `lib()` raises.
+
+(The directory name contains '-', so import it as `sblas_b200` via the alias module
+at the repo root.)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsblas_spmv.so")
+
+BASELINE, V1, V2 = 0, 1, 2
+SRC_HOST, SRC_DEVICE_SHARD = 0, 1
+K_VECTOR, K_TILE = 1, 2
+COLS_PREFIX, COLS_BANDED, COLS_UNIFORM, COLS_CIRCUIT = 0, 1, 2, 3
+
+_LL = C.c_longlong
+_vp = C.c_void_p
+
+
+class Part(C.Structure):
+    """struct sblas_part (include/sblas_spmv.h) == the partition fields of struct spmv_task."""
+    _fields_ = [("start_idx", _LL), ("end_idx", _LL), ("start_row", C.c_int), ("end_row", C.c_int),
+                ("start_flag", C.c_int), ("end_flag", C.c_int), ("dev_m", C.c_int), ("dev_nnz", C.c_int)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+class SegArgs(C.Structure):
+    """struct sblas_seg_args (include/sblas_device.h)."""
+    _fields_ = [("val", _vp), ("col", _vp), ("rowptr", _vp), ("x", _vp), ("y", _vp), ("edge", _vp),
+                ("carry", _vp), ("tail", _vp), ("tstart", _vp), ("alpha", C.c_double), ("beta", C.c_double),
+                ("row_lo", C.c_int), ("row_hi", C.c_int), ("nz0", C.c_int), ("nz1", C.c_int),
+                ("skip_first", C.c_int), ("skip_last", C.c_int), ("tile0", C.c_int), ("ntile", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libsblas_spmv.so.  Raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libsblas_spmv.so is not built (run `make` or __graft_entry__.build()): " + LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    mg = [C.c_int, C.c_int, _LL, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]
+    for name, extra in (("baseline", []), ("v1", [C.c_int]), ("v2", [C.c_int, _LL, C.c_int])):
+        for pre in ("sblas_spmv_mgpu_", "spMV_mgpu_"):
+            f = getattr(L, pre + name)
+            f.argtypes = mg + extra
+            f.restype = C.c_int
+    L.sblas_get_row_from_index.argtypes = [C.c_int, _vp, _LL]
+    L.sblas_get_time.restype = C.c_double
+    L.sblas_get_gpu_availble_mem.argtypes = [C.c_int]
+    L.sblas_get_gpu_availble_mem.restype = C.c_double
+    L.sblas_partition_baseline.argtypes = [C.c_int, _vp, C.c_int, P(Part)]
+    L.sblas_partition_v1.argtypes = [C.c_int, _LL, _vp, C.c_int, P(Part)]
+    L.sblas_v2_num_tasks.argtypes = [_LL, _LL]
+    L.sblas_generate_tasks_v2.argtypes = [C.c_int, _LL, _vp, _LL, P(Part)]
+    L.sblas_v2_task_owner.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.sblas_local_rowptr.argtypes = [_vp, P(Part), C.c_int, _vp]
+    L.sblas_local_rowptr.restype = None
+    L.sblas_spmv_plan_create.argtypes = [P(_vp), C.c_int, C.c_int, C.c_int, _LL, _vp, _vp, _vp, C.c_int, C.c_int,
+                                         _LL, C.c_int]
+    L.sblas_spmv_plan_create_rank.argtypes = [P(_vp), C.c_int, C.c_int, C.c_int, _LL, _vp, _vp, _vp, C.c_int,
+                                              C.c_int, C.c_int, C.c_int, _LL, C.c_int, C.c_int]
+    L.sblas_spmv_plan_execute.argtypes = [_vp, P(C.c_double), _vp, P(C.c_double), _vp]
+    L.sblas_spmv_plan_execute_device.argtypes = [_vp, C.c_double, C.c_double, C.c_int]
+    L.sblas_spmv_plan_num_devices.argtypes = [_vp]
+    L.sblas_spmv_plan_num_segments.argtypes = [_vp]
+    L.sblas_spmv_plan_segment.argtypes = [_vp, C.c_int, P(Part), P(C.c_int)]
+    L.sblas_spmv_plan_x.argtypes = [_vp, C.c_int]
+    L.sblas_spmv_plan_x.restype = _vp
+    L.sblas_spmv_plan_y.argtypes = [_vp, C.c_int, P(C.c_int), P(C.c_int)]
+    L.sblas_spmv_plan_y.restype = _vp
+    L.sblas_spmv_plan_rowptr.argtypes = [_vp, C.c_int, P(C.c_int)]
+    L.sblas_spmv_plan_rowptr.restype = _vp
+    L.sblas_spmv_plan_stream.argtypes = [_vp, C.c_int]
+    L.sblas_spmv_plan_stream.restype = _vp
+    L.sblas_spmv_plan_edges.argtypes = [_vp, _vp]
+    L.sblas_spmv_plan_edge_ptr.argtypes = [_vp, C.c_int]
+    L.sblas_spmv_plan_edge_ptr.restype = _vp
+    L.sblas_spmv_plan_edge_slots.argtypes = [_vp]
+    L.sblas_spmv_plan_merge_gathered.argtypes = [_vp, _vp, C.c_double, C.c_double]
+    L.sblas_spmv_plan_bind_edge_table.argtypes = [_vp, _vp]
+    L.sblas_memcpy.argtypes = [_vp, _vp, C.c_ulonglong, C.c_int]
+    L.sblas_spmv_plan_alg_bytes.argtypes = [_vp, C.c_int, _LL]
+    L.sblas_spmv_plan_alg_bytes.restype = C.c_double
+    L.sblas_spmv_plan_launches.argtypes = [_vp]
+    L.sblas_spmv_plan_destroy.argtypes = [_vp]
+    L.sblas_spmv_plan_destroy.restype = None
+    L.sblas_last_error.restype = C.c_char_p
+    L.sblas_tile_size.argtypes = [C.c_int]
+    L.sblas_launch_rebase_rowptr.argtypes = [_vp, _LL, C.c_int, _LL, _vp, _vp]
+    L.sblas_launch_tile_rows.argtypes = [P(SegArgs), C.c_int, _vp, _vp]
+    L.sblas_launch_spmv_segment.argtypes = [P(SegArgs), C.c_int, C.c_int, C.c_int, _vp]
+    L.sblas_launch_edge_merge.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_double, C.c_double, _vp]
+    L.sblas_launch_fill_f64.argtypes = [_vp, _LL, C.c_double, _vp]
+    L.sblas_synth_fill_csr.argtypes = [_vp, C.c_int, C.c_int, _LL, _LL, C.c_int, C.c_int, _LL, C.c_ulonglong,
+                                       C.c_int, C.c_double, _vp, _vp, _vp]
+    L.sblas_synth_fill_uniform.argtypes = [_vp, _LL, C.c_ulonglong, C.c_double, C.c_double, _vp]
+    _lib = L
+    return L
+
+
+def last_error():
+    return (lib().sblas_last_error() or b"").decode()
+
+
+# ----------------------------------------------------------------------------- helpers
+def _host(a, dt, name):
+    a = np.asarray(a)
+    if a.dtype != dt or not a.flags["C_CONTIGUOUS"]:
+        raise TypeError("%s must be a C-contiguous numpy array of %s (like the reference's host buffers)" % (name, dt))
+    return a
+
+
+def _ptr(a):
+    return a.ctypes.data if isinstance(a, np.ndarray) else int(a)
+
+
+# ----------------------------------------------------------------------------- reference entry points
+def spMV_mgpu_baseline(m, n, nnz, alpha, csrVal, csrRowPtr, csrColIndex, x, beta, y, ngpu):
+    """spmv/include/spmv_kernel.h:11-15.  y (numpy float64) is updated in place; returns the status code."""
+    a, b = C.c_double(alpha), C.c_double(beta)
+    return lib().spMV_mgpu_baseline(m, n, nnz, C.addressof(a), _ptr(_host(csrVal, np.float64, "csrVal")),
+                                    _ptr(_host(csrRowPtr, np.int64, "csrRowPtr")),
+                                    _ptr(_host(csrColIndex, np.int32, "csrColIndex")),
+                                    _ptr(_host(x, np.float64, "x")), C.addressof(b),
+                                    _ptr(_host(y, np.float64, "y")), ngpu)
+
+
+def spMV_mgpu_v1(m, n, nnz, alpha, csrVal, csrRowPtr, csrColIndex, x, beta, y, ngpu, kernel):
+    """spmv/include/spmv_kernel.h:16-21."""
+    a, b = C.c_double(alpha), C.c_double(beta)
+    return lib().spMV_mgpu_v1(m, n, nnz, C.addressof(a), _ptr(_host(csrVal, np.float64, "csrVal")),
+                              _ptr(_host(csrRowPtr, np.int64, "csrRowPtr")),
+                              _ptr(_host(csrColIndex, np.int32, "csrColIndex")),
+                              _ptr(_host(x, np.float64, "x")), C.addressof(b),
+                              _ptr(_host(y, np.float64, "y")), ngpu, kernel)
+
+
+def spMV_mgpu_v2(m, n, nnz, alpha, csrVal, csrRowPtr, csrColIndex, x, beta, y, ngpu, kernel, nb, copy_of_workspace):
+    """spmv/include/spmv_kernel.h:23-30."""
+    a, b = C.c_double(alpha), C.c_double(beta)
+    return lib().spMV_mgpu_v2(m, n, nnz, C.addressof(a), _ptr(_host(csrVal, np.float64, "csrVal")),
+                              _ptr(_host(csrRowPtr, np.int64, "csrRowPtr")),
+                              _ptr(_host(csrColIndex, np.int32, "csrColIndex")),
+                              _ptr(_host(x, np.float64, "x")), C.addressof(b),
+                              _ptr(_host(y, np.float64, "y")), ngpu, kernel, int(nb), copy_of_workspace)
+
+
+def get_row_from_index(n, a, idx):
+    """spmv/include/spmv_kernel.h:32."""
+    return lib().sblas_get_row_from_index(n, _ptr(_host(a, np.int64, "a")), int(idx))
+
+
+def get_time():
+    return lib().sblas_get_time()
+
+
+def get_gpu_availble_mem(ngpu):
+    return lib().sblas_get_gpu_availble_mem(ngpu)
+
+
+# ----------------------------------------------------------------------------- partitioners
+def _parts_to_dict(arr, count):
+    keys = [k for k, _ in Part._fields_]
+    out = {k: np.zeros(count, np.int64 if k.endswith("idx") else np.int32) for k in keys}
+    for i in range(count):
+        for k in keys:
+            out[k][i] = getattr(arr[i], k)
+    return out
+
+
+def partition_baseline(csrRowPtr, ngpu):
+    rp = _host(csrRowPtr, np.int64, "csrRowPtr")
+    arr = (Part * ngpu)()
+    rc = lib().sblas_partition_baseline(len(rp) - 1, _ptr(rp), ngpu, arr)
+    assert rc == 0
+    return _parts_to_dict(arr, ngpu)
+
+
+def partition_v1(csrRowPtr, ngpu):
+    rp = _host(csrRowPtr, np.int64, "csrRowPtr")
+    arr = (Part * ngpu)()
+    rc = lib().sblas_partition_v1(len(rp) - 1, int(rp[-1]), _ptr(rp), ngpu, arr)
+    assert rc == 0
+    return _parts_to_dict(arr, ngpu)
+
+
+def generate_tasks_v2(csrRowPtr, nb):
+    rp = _host(csrRowPtr, np.int64, "csrRowPtr")
+    T = lib().sblas_v2_num_tasks(int(rp[-1]), int(nb))
+    arr = (Part * max(T, 1))()
+    got = lib().sblas_generate_tasks_v2(len(rp) - 1, int(rp[-1]), _ptr(rp), int(nb), arr)
+    assert got == T
+    return _parts_to_dict(arr, T)
+
+
+def v2_task_owner(T, ngpu, task):
+    return lib().sblas_v2_task_owner(T, ngpu, task)
+
+
+def local_rowptr(csrRowPtr, part, baseline=False):
+    rp = _host(csrRowPtr, np.int64, "csrRowPtr")
+    p = Part(**{k: int(part[k]) for k, _ in Part._fields_})
+    out = np.zeros(p.dev_m + 1, np.int32)
+    lib().sblas_local_rowptr(_ptr(rp), C.byref(p), 1 if baseline else 0, _ptr(out))
+    return out
+
+
+# ----------------------------------------------------------------------------- plan
+class Plan:
+    """Resident multi-GPU SpMV plan (include/sblas_spmv.h, plan API)."""
+
+    def __init__(self, handle, m, n, keep=()):
+        self._h = handle
+        self.m, self.n = m, n
+        self._keep = keep          # arrays that must outlive the plan (adopted device shards)
+
+    @classmethod
+    def create(cls, version, m, n, nnz, csrVal, csrRowPtr, csrColIndex, ngpu, kernel=1, nb=0, q=1):
+        h = _vp()
+        rc = lib().sblas_spmv_plan_create(C.byref(h), version, m, n, nnz,
+                                          _ptr(_host(csrVal, np.float64, "csrVal")),
+                                          _ptr(_host(csrRowPtr, np.int64, "csrRowPtr")),
+                                          _ptr(_host(csrColIndex, np.int32, "csrColIndex")), ngpu, kernel, int(nb), q)
+        if rc != 0:
+            raise RuntimeError("sblas_spmv_plan_create rc=%d: %s" % (rc, last_error()))
+        return cls(h, m, n)
+
+    @classmethod
+    def create_rank(cls, version, m, n, nnz, csrVal, csrRowPtr, csrColIndex, world, rank, device, kernel=1,
+                    nb=0, q=1, flags=SRC_HOST, keep=()):
+        """csrVal / csrColIndex: numpy host arrays (SRC_HOST) or integer device pointers (SRC_DEVICE_SHARD)."""
+        h = _vp()
+        rc = lib().sblas_spmv_plan_create_rank(C.byref(h), version, m, n, nnz, _ptr(csrVal),
+                                               _ptr(_host(csrRowPtr, np.int64, "csrRowPtr")), _ptr(csrColIndex),
+                                               world, rank, device, kernel, int(nb), q, flags)
+        if rc != 0:
+            raise RuntimeError("sblas_spmv_plan_create_rank rc=%d: %s" % (rc, last_error()))
+        return cls(h, m, n, keep)
+
+    def execute(self, alpha, x, beta, y):
+        a, b = C.c_double(alpha), C.c_double(beta)
+        rc = lib().sblas_spmv_plan_execute(self._h, C.byref(a), _ptr(x), C.byref(b), _ptr(y))
+        if rc != 0:
+            raise RuntimeError("sblas_spmv_plan_execute rc=%d: %s" % (rc, last_error()))
+
+    def execute_device(self, alpha, beta, sync=False):
+        rc = lib().sblas_spmv_plan_execute_device(self._h, alpha, beta, 1 if sync else 0)
+        if rc != 0:
+            raise RuntimeError("sblas_spmv_plan_execute_device rc=%d: %s" % (rc, last_error()))
+
+    def merge_gathered(self, gathered_ptr, alpha, beta):
+        rc = lib().sblas_spmv_plan_merge_gathered(self._h, int(gathered_ptr), alpha, beta)
+        if rc != 0:
+            raise RuntimeError("sblas_spmv_plan_merge_gathered rc=%d: %s" % (rc, last_error()))
+
+    @property
+    def num_devices(self):
+        return lib().sblas_spmv_plan_num_devices(self._h)
+
+    @property
+    def num_segments(self):
+        return lib().sblas_spmv_plan_num_segments(self._h)
+
+    def segment(self, i):
+        p, d = Part(), C.c_int()
+        assert lib().sblas_spmv_plan_segment(self._h, i, C.byref(p), C.byref(d)) == 0
+        out = p.as_dict()
+        out["device"] = d.value
+        return out
+
+    def x_ptr(self, dev=0):
+        return lib().sblas_spmv_plan_x(self._h, dev)
+
+    def y_ptr(self, dev=0):
+        fr, rows = C.c_int(), C.c_int()
+        p = lib().sblas_spmv_plan_y(self._h, dev, C.byref(fr), C.byref(rows))
+        return p, fr.value, rows.value
+
+    def rowptr_ptr(self, dev=0):
+        cnt = C.c_int()
+        p = lib().sblas_spmv_plan_rowptr(self._h, dev, C.byref(cnt))
+        return p, cnt.value
+
+    def stream(self, dev=0):
+        return lib().sblas_spmv_plan_stream(self._h, dev)
+
+    def edge_ptr(self, dev=0):
+        return lib().sblas_spmv_plan_edge_ptr(self._h, dev)
+
+    def bind_edge_table(self, device_ptr):
+        assert lib().sblas_spmv_plan_bind_edge_table(self._h, int(device_ptr)) == 0
+
+    @property
+    def edge_slots(self):
+        return lib().sblas_spmv_plan_edge_slots(self._h)
+
+    def edges(self):
+        out = np.zeros(2 * self.num_segments, np.float64)
+        assert lib().sblas_spmv_plan_edges(self._h, _ptr(out)) == 0
+        return out
+
+    def alg_bytes(self, beta_nonzero, x_touched_per_gpu=-1):
+        return lib().sblas_spmv_plan_alg_bytes(self._h, 1 if beta_nonzero else 0, int(x_touched_per_gpu))
+
+    @property
+    def launches(self):
+        return lib().sblas_spmv_plan_launches(self._h)
+
+    def destroy(self):
+        if self._h:
+            lib().sblas_spmv_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def memcpy(dst, src, nbytes, kind):
+    """kind: 1 H2D, 2 D2H, 3 D2D (blocking).  dst/src: numpy arrays or integer device pointers."""
+    rc = lib().sblas_memcpy(_ptr(dst), _ptr(src), int(nbytes), kind)
+    if rc != 0:
+        raise RuntimeError("sblas_memcpy: cuda error %d" % rc)
+
+
+def device_synchronize():
+    rc = lib().sblas_device_synchronize()
+    if rc != 0:
+        raise RuntimeError("cudaDeviceSynchronize: cuda error %d" % rc)
+
+
+# ----------------------------------------------------------------------------- synthetic content (device)
+def synth_fill_csr(d_rowptr, row_first, nrows, k0, k1, n, cols_mode, band, seed, d_val, d_col, value_const=None,
+                   stream=None):
+    rc = lib().sblas_synth_fill_csr(int(d_rowptr), row_first, nrows, int(k0), int(k1), n, cols_mode, int(band),
+                                    int(seed), 0 if value_const is None else 1,
+                                    0.0 if value_const is None else float(value_const), int(d_val), int(d_col),
+                                    stream)
+    if rc != 0:
+        raise RuntimeError("sblas_synth_fill_csr: cuda error %d" % rc)
+
+
+def synth_fill_uniform(d_p, count, seed, lo=0.0, hi=1.0, stream=None):
+    rc = lib().sblas_synth_fill_uniform(int(d_p), int(count), int(seed), lo, hi, stream)
+    if rc != 0:
+        raise RuntimeError("sblas_synth_fill_uniform: cuda error %d" % rc)

@@ -1,0 +1,51 @@
+/* sblas_internal.h -- plan data structures (host C). Not part of the C-ABI. */
+#ifndef SBLAS_INTERNAL_H
+#define SBLAS_INTERNAL_H
+#include <cuda_runtime_api.h>
+#include "sblas_device.h"
+#include "sblas_spmv.h"
+
+/* one live segment held by this process (a v1 shard, a v2 task, a baseline block) */
+typedef struct sblas_seg {
+    int gidx;              /* index in the global partition (plan->parts)       */
+    int dev;               /* index of the GPU inside the plan                  */
+    int lidx;              /* index among that GPU's segments                   */
+    int stream;            /* which of the GPU's q streams runs it              */
+    long long tile_off;    /* offset of its tile metadata in the GPU's arrays   */
+    sblas_seg_args args;
+} sblas_seg;
+
+/* one GPU of the plan: a contiguous resident nnz range and the rows it touches */
+typedef struct sblas_dev {
+    int device;                       /* CUDA ordinal */
+    int seg_begin, seg_end;           /* plan->segs[seg_begin, seg_end) live here (-1: none) */
+    long long first_idx, last_idx;    /* global nnz range, inclusive */
+    int first_row, last_row, rows, nnz;
+    double *d_val; int *d_col; int own_matrix;
+    int *d_rowptr; double *d_x; double *d_y;
+    double *d_edge; int edge_is_host, edge_bound; void *h_edge_alloc;
+    double *d_carry, *d_tail; int *d_tstart;
+    /* merge lists of the split rows this GPU owns */
+    int nmerge, nmsrc;
+    int *d_mrow, *d_mbeg; const double **d_msrc;
+    int *h_mrow, *h_mbeg; const double **h_msrc; long long *h_msrc_off;
+    cudaStream_t *streams; int nstreams;
+    cudaEvent_t *ev_seg, ev_in, ev_done;
+    int kind, ipt;
+    long long xs_lo, xs_hi;           /* slice of x this GPU uploads itself */
+} sblas_dev;
+
+struct sblas_spmv_plan {
+    int version, m, n, kernel, q, world, rank, rank_mode, ndev, p2p;
+    long long nnz, nb;
+    /* global partition, identical on every rank */
+    int nparts; sblas_part *parts;
+    int *g_owner, *g_local, *g_lo, *g_hi, *g_sf, *g_sl;
+    int max_local;
+    int nseg; sblas_seg *segs;
+    sblas_dev *devs;
+    const double *gather_base;
+};
+
+void sblas_set_error(const char *fmt, const char *a, const char *b, int line);
+#endif

@@ -1,0 +1,405 @@
+/* sblas_kernels.cu -- hand-written sm_100a kernels for double-precision CSR SpMV,
+ * y = alpha*A*x + beta*y, replacing the cusparseDcsrmv / cusparseDcsrmv_mp calls
+ * of the reference (spmv/src/dspmv_mgpu_baseline.cu:163, dspmv_mgpu_v1.cu:200,206,
+ * dspmv_mgpu_v2.cu:351,357) and the disabled CSR5 back-end
+ * (spmv/include/detail/cuda/csr5_spmv_cuda.h).
+ *
+ * The work is HBM-bound (12 B per nnz streamed once, 2 flop per nnz): no tensor
+ * cores.  What matters is bytes in flight per SM, fully coalesced 128/256-bit
+ * streaming loads that bypass L1, x served from L1/L2, and an nnz-balanced grid.
+ *
+ *  spmv_tile_kernel   nnz-balanced tiles (256 threads x IPT nnz).  val is streamed
+ *                     with 256-bit and col with 128-bit ld.global.nc.L1::no_allocate
+ *                     loads, always aligned because tiles sit on absolute multiples
+ *                     of the tile size.  Per tile the reduction strategy adapts to the
+ *                     rows inside it: whole tile inside <=2 rows -> block reduction
+ *                     from registers (the "block per long row" case); otherwise
+ *                     products go to shared memory and G = 1..32 lanes reduce each
+ *                     row (thread-per-row for short rows ... warp-per-row).
+ *                     Rows that leave a tile are finished by spmv_tile_fixup in a
+ *                     fixed order (deterministic; no floating-point atomics).
+ *  spmv_vec_kernel    LANES (2..32) lanes per row, for small inputs and as the
+ *                     simple cross-check path.
+ */
+#include <stdint.h>
+#include "sblas_device.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ void ldg_nc_i4(const int *p, int &a, int &b, int &c, int &d)
+{
+    asm("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+        : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
+}
+/* 256-bit load (LDG.E.256 on sm_100a) */
+__device__ __forceinline__ void ldg_nc_d4(const double *p, double &a, double &b, double &c, double &d)
+{
+    asm("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+        : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+/* write one finished row: edge rows (split between segments) keep their raw sum
+ * for the ordered merge (reference merge: dspmv_mgpu_v1.cu:235-248,
+ * dspmv_mgpu_v2.cu:385-441); beta == 0 does not read y (csrmv convention). */
+__device__ __forceinline__ void emit_row(const sblas_seg_args &a, int r, double s)
+{
+    if (r == a.skip_first) {
+        a.edge[0] = s;
+    } else if (r == a.skip_last) {
+        a.edge[1] = s;
+    } else {
+        double out = a.alpha * s;
+        if (a.beta != 0.0) out += a.beta * a.y[r];
+        a.y[r] = out;
+    }
+}
+
+/* ------------------------------------------------------------------ vector kernel */
+template <int LANES>
+__global__ void __launch_bounds__(kThreads) spmv_vec_kernel(const sblas_seg_args a)
+{
+    const int lane = threadIdx.x & (LANES - 1);
+    const long long gid = ((long long)blockIdx.x * kThreads + threadIdx.x) / LANES;
+    const long long nrows = (long long)a.row_hi - a.row_lo + 1;
+    const bool live = gid < nrows;
+    const int r = a.row_lo + (int)(live ? gid : 0);
+    int lo = 0, hi = 0;
+    if (live) {
+        lo = max(__ldg(a.rowptr + r), a.nz0);
+        hi = min(__ldg(a.rowptr + r + 1), a.nz1);
+    }
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int k = lo + lane;
+    for (; k + 3 * LANES < hi; k += 4 * LANES) {
+        const int c0 = __ldg(a.col + k), c1 = __ldg(a.col + k + LANES);
+        const int c2 = __ldg(a.col + k + 2 * LANES), c3 = __ldg(a.col + k + 3 * LANES);
+        const double v0 = __ldg(a.val + k), v1 = __ldg(a.val + k + LANES);
+        const double v2 = __ldg(a.val + k + 2 * LANES), v3 = __ldg(a.val + k + 3 * LANES);
+        s0 += v0 * __ldg(a.x + c0);
+        s1 += v1 * __ldg(a.x + c1);
+        s2 += v2 * __ldg(a.x + c2);
+        s3 += v3 * __ldg(a.x + c3);
+    }
+    for (; k < hi; k += LANES) s0 += __ldg(a.val + k) * __ldg(a.x + __ldg(a.col + k));
+    double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int off = LANES >> 1; off > 0; off >>= 1) s += __shfl_xor_sync(kFull, s, off);
+    if (live && lane == 0) emit_row(a, r, s);
+}
+
+/* ------------------------------------------------------------------ tile kernel */
+template <int IPT>
+struct TileCfg {
+    static constexpr int kTile = kThreads * IPT;
+    static constexpr int kGroups = IPT / 4;          /* 4 consecutive nnz per thread per group */
+    static constexpr int kBBCap = kTile + 8;         /* row boundaries staged per pass        */
+    static constexpr int kSmem = kTile * 8 + kBBCap * 4;
+};
+
+template <int IPT>
+__global__ void __launch_bounds__(kThreads, (IPT <= 8 ? 4 : 2)) spmv_tile_kernel(const sblas_seg_args a)
+{
+    using Cfg = TileCfg<IPT>;
+    constexpr int TILE = Cfg::kTile;
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    double *P = reinterpret_cast<double *>(smem_raw);
+    int *BB = reinterpret_cast<int *>(smem_raw + (size_t)TILE * 8);
+    __shared__ double red[2][kThreads / 32];
+
+    const int j = blockIdx.x;
+    const int t = threadIdx.x;
+    const long long base = (long long)(a.tile0 + j) * TILE;           /* GPU-local nnz index */
+    const int T0 = (int)max((long long)a.nz0, base);
+    const int T1 = (int)min((long long)a.nz1, base + TILE);
+    const bool full = (T0 == base) && ((long long)T1 == base + TILE);
+
+    /* rows that start in this tile: [rs, re) */
+    const int rs = __ldg(a.tstart + j), re = __ldg(a.tstart + j + 1);
+    const int nown = re - rs;
+
+    double p[IPT];
+    const double *vbase = a.val + base;
+    const int *cbase = a.col + base;
+    if (full) {
+        int c[IPT];
+        double v[IPT];
+#pragma unroll
+        for (int g = 0; g < Cfg::kGroups; ++g) {
+            const int e = g * (kThreads * 4) + 4 * t;
+            ldg_nc_i4(cbase + e, c[4 * g], c[4 * g + 1], c[4 * g + 2], c[4 * g + 3]);
+            ldg_nc_d4(vbase + e, v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        }
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) p[i] = v[i] * __ldg(a.x + c[i]);
+    } else {
+#pragma unroll
+        for (int g = 0; g < Cfg::kGroups; ++g) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const long long pos = base + g * (kThreads * 4) + 4 * t + i;
+                double prod = 0.0;
+                if (pos >= T0 && pos < T1) prod = __ldg(a.val + pos) * __ldg(a.x + __ldg(a.col + pos));
+                p[4 * g + i] = prod;
+            }
+        }
+    }
+
+    /* does the last row that starts here continue into the next tile? */
+    bool ext = false;
+    if (nown > 0) ext = min(__ldg(a.rowptr + re), a.nz1) > T1;
+
+    if (nown <= 1) {
+        /* ---- mode A: at most one row boundary inside the tile: reduce from registers */
+        int split = T1;
+        if (nown == 1) split = min(max(__ldg(a.rowptr + rs), T0), T1);
+        const int lsplit = (int)(split - base);                     /* tile-local */
+        double sc = 0.0, so = 0.0;
+#pragma unroll
+        for (int g = 0; g < Cfg::kGroups; ++g) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int e = g * (kThreads * 4) + 4 * t + i;
+                if (e < lsplit) sc += p[4 * g + i]; else so += p[4 * g + i];
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            sc += __shfl_xor_sync(kFull, sc, off);
+            so += __shfl_xor_sync(kFull, so, off);
+        }
+        if ((t & 31) == 0) { red[0][t >> 5] = sc; red[1][t >> 5] = so; }
+        __syncthreads();
+        if (t == 0) {
+            double c = 0.0, o = 0.0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) { c += red[0][w]; o += red[1][w]; }
+            a.carry[j] = c;
+            if (nown == 1) {
+                if (ext) a.tail[j] = o; else emit_row(a, rs, o);
+            }
+        }
+        return;
+    }
+
+    /* ---- mode S: products to shared memory, G lanes per row */
+#pragma unroll
+    for (int g = 0; g < Cfg::kGroups; ++g) {
+        const int e = g * (kThreads * 4) + 4 * t;
+        *reinterpret_cast<double2 *>(P + e) = make_double2(p[4 * g], p[4 * g + 1]);
+        *reinterpret_cast<double2 *>(P + e + 2) = make_double2(p[4 * g + 2], p[4 * g + 3]);
+    }
+    const int nseg = nown + 1;                 /* segment 0 = the row left open by tile j-1 */
+    const int avg = (T1 - T0) / nseg;
+    int G = 1;
+    while (G < 32 && G * 8 <= avg) G <<= 1;
+    const int ngroups = kThreads / G;
+    const int grp = t / G, lane = t & (G - 1);
+
+    for (int c0 = 0; c0 < nseg; c0 += Cfg::kBBCap - 1) {
+        const int cn = min(nseg - c0, Cfg::kBBCap - 1);
+        __syncthreads();                        /* P written / previous pass done with BB */
+        for (int idx = t; idx <= cn; idx += kThreads) {
+            const int s = c0 + idx;             /* boundary s: start of segment s */
+            int b = T0;
+            if (s > 0) b = min(max(__ldg(a.rowptr + rs + s - 1), T0), T1);
+            BB[idx] = (int)(b - base);
+        }
+        __syncthreads();
+        for (int s0 = 0; s0 < cn; s0 += ngroups) {
+            const int s = s0 + grp;
+            double acc = 0.0;
+            if (s < cn) {
+                const int b = BB[s], e = BB[s + 1];
+                double acc1 = 0.0;
+                int k = b + lane;
+                for (; k + G < e; k += 2 * G) { acc += P[k]; acc1 += P[k + G]; }
+                if (k < e) acc += P[k];
+                acc += acc1;
+            }
+            for (int off = G >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(kFull, acc, off);
+            if (s < cn && lane == 0) {
+                const int gs = c0 + s;
+                if (gs == 0) {
+                    a.carry[j] = acc;
+                } else if (gs == nown && ext) {
+                    a.tail[j] = acc;
+                } else {
+                    emit_row(a, rs + gs - 1, acc);
+                }
+            }
+        }
+    }
+}
+
+/* rows that leave their tile: y[r] = alpha*(tail[j] + carry[j+1] + ... ) + beta*y[r],
+ * one warp per tile, fixed summation order (the CSR5 "calibrator" step,
+ * csr5_spmv_cuda.h:313-382, without atomics). */
+__global__ void __launch_bounds__(kThreads) spmv_tile_fixup(const sblas_seg_args a, int tile)
+{
+    const int j = (int)(((long long)blockIdx.x * kThreads + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (j >= a.ntile) return;
+    const int rs = __ldg(a.tstart + j), re = __ldg(a.tstart + j + 1);
+    if (re == rs) return;
+    const int r = re - 1;
+    const long long T1 = min((long long)a.nz1, (long long)(a.tile0 + j + 1) * tile);
+    const int e = min(__ldg(a.rowptr + r + 1), a.nz1);
+    if ((long long)e <= T1) return;
+    const int jend = (e - 1) / tile - a.tile0;
+    double acc = 0.0;
+    for (int i = j + 1 + lane; i <= jend; i += 32) acc += a.carry[i];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(kFull, acc, off);
+    if (lane == 0) emit_row(a, r, a.tail[j] + acc);
+}
+
+/* ------------------------------------------------------------------ plan helpers */
+__global__ void tile_rows_kernel(const sblas_seg_args a, int tile, int *tstart)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > a.ntile) return;
+    int out;
+    if (j == 0) {
+        out = a.row_lo;
+    } else if (j == a.ntile) {
+        out = a.row_hi + 1;
+    } else {
+        const long long T0 = (long long)(a.tile0 + j) * tile;
+        int lo = a.row_lo, hi = a.row_hi + 1;            /* first r in [lo,hi] with rowptr[r] >= T0 */
+        while (lo < hi) {
+            const int mid = lo + ((hi - lo) >> 1);
+            if ((long long)__ldg(a.rowptr + mid) < T0) lo = mid + 1; else hi = mid;
+        }
+        out = lo;
+    }
+    tstart[j] = out;
+}
+
+__global__ void rebase_rowptr_kernel(const long long *__restrict__ rp64, long long first_idx, int total,
+                                     long long count, int *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    long long v = rp64[i] - first_idx;
+    v = v < 0 ? 0 : (v > total ? total : v);
+    out[i] = (int)v;
+}
+
+__global__ void edge_merge_kernel(const int *__restrict__ mrow, const int *__restrict__ mbeg,
+                                  const double *const *__restrict__ msrc, int nmerge, double *y, double alpha,
+                                  double beta)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nmerge) return;
+    double s = 0.0;
+    for (int k = mbeg[i]; k < mbeg[i + 1]; ++k) s += *reinterpret_cast<const volatile double *>(msrc[k]);
+    const int r = mrow[i];
+    double out = alpha * s;
+    if (beta != 0.0) out += beta * y[r];
+    y[r] = out;
+}
+
+__global__ void fill_f64_kernel(double *p, long long n, double v)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+template <int IPT>
+cudaError_t launch_tile(const sblas_seg_args *a, cudaStream_t s)
+{
+    using Cfg = TileCfg<IPT>;
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(spmv_tile_kernel<IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::kSmem);
+        if (e != cudaSuccess) return e;
+        attr_done[dev] = true;
+    }
+    spmv_tile_kernel<IPT><<<a->ntile, kThreads, Cfg::kSmem, s>>>(*a);
+    const long long warps = a->ntile;
+    const int blocks = (int)((warps * 32 + kThreads - 1) / kThreads);
+    spmv_tile_fixup<<<blocks, kThreads, 0, s>>>(*a, Cfg::kTile);
+    return cudaGetLastError();
+}
+
+template <int LANES>
+cudaError_t launch_vec(const sblas_seg_args *a, cudaStream_t s)
+{
+    const long long nrows = (long long)a->row_hi - a->row_lo + 1;
+    const long long blocks = (nrows * LANES + kThreads - 1) / kThreads;
+    spmv_vec_kernel<LANES><<<(unsigned)blocks, kThreads, 0, s>>>(*a);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" int sblas_tile_size(int ipt) { return kThreads * ipt; }
+
+extern "C" cudaError_t sblas_launch_rebase_rowptr(const long long *rp64, long long first_idx, int total_nnz,
+                                                  long long count, int *out, cudaStream_t s)
+{
+    if (count <= 0) return cudaSuccess;
+    const long long blocks = (count + 255) / 256;
+    rebase_rowptr_kernel<<<(unsigned)blocks, 256, 0, s>>>(rp64, first_idx, total_nnz, count, out);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t sblas_launch_tile_rows(const sblas_seg_args *a, int tile, int *tstart_out, cudaStream_t s)
+{
+    const int n = a->ntile + 1;
+    tile_rows_kernel<<<(n + 255) / 256, 256, 0, s>>>(*a, tile, tstart_out);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t sblas_launch_edge_merge(const int *mrow, const int *mbeg, const double *const *msrc,
+                                               int nmerge, double *y, double alpha, double beta, cudaStream_t s)
+{
+    if (nmerge <= 0) return cudaSuccess;
+    edge_merge_kernel<<<(nmerge + 127) / 128, 128, 0, s>>>(mrow, mbeg, msrc, nmerge, y, alpha, beta);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t sblas_launch_fill_f64(double *p, long long n, double v, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    fill_f64_kernel<<<(unsigned)blocks, 256, 0, s>>>(p, n, v);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t sblas_launch_spmv_segment(const sblas_seg_args *a, int kind, int ipt, int lanes,
+                                                 cudaStream_t s)
+{
+    const long long nrows = (long long)a->row_hi - a->row_lo + 1;
+    if (nrows <= 0) return cudaSuccess;
+    const long long nnz = (long long)a->nz1 - a->nz0;
+    if (kind == SBLAS_K_TILE && nnz > 0 && a->ntile > 0) {
+        switch (ipt) {
+        case 4: return launch_tile<4>(a, s);
+        case 8: return launch_tile<8>(a, s);
+        case 16: return launch_tile<16>(a, s);
+        default: return cudaErrorInvalidValue;
+        }
+    }
+    if (lanes <= 0) {
+        const long long mean = nnz / nrows;
+        lanes = 2;
+        while (lanes < 32 && lanes * 2 <= mean) lanes <<= 1;
+    }
+    switch (lanes) {
+    case 2: return launch_vec<2>(a, s);
+    case 4: return launch_vec<4>(a, s);
+    case 8: return launch_vec<8>(a, s);
+    case 16: return launch_vec<16>(a, s);
+    case 32: return launch_vec<32>(a, s);
+    default: return cudaErrorInvalidValue;
+    }
+}

@@ -1,0 +1,751 @@
+/* sblas_plan.c -- host side (C) of the multi-GPU CSR SpMV path.
+ *
+ * Replaces the bodies of spMV_mgpu_baseline / _v1 / _v2
+ * (spmv/src/dspmv_mgpu_baseline.cu:14-214, dspmv_mgpu_v1.cu:16-280,
+ * dspmv_mgpu_v2.cu:33-207) with a plan/execute split:
+ *
+ *   plan   = reference partition (sblas_partition.c) -> segments -> one contiguous
+ *            resident nnz range per GPU (val, col uploaded once), int32 row pointer
+ *            rebased on the GPU, tile metadata, merge lists for split rows.
+ *   execute= x replicated (sliced H2D + NVLink all-gather when several GPUs are
+ *            driven from this process), one launch per segment, then ONE merge
+ *            kernel per GPU that finishes rows split between segments in ascending
+ *            segment order, reading the other GPUs' partial sums over NVLink P2P
+ *            (reference: host loops dspmv_mgpu_v1.cu:235-248, dspmv_mgpu_v2.cu:385-441).
+ *
+ * There is no CPU arithmetic on this path and no CPU fallback.
+ */
+#include <cuda_runtime_api.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/time.h>
+#include "sblas_device.h"
+#include "sblas_internal.h"
+#include "sblas_spmv.h"
+
+static __thread char g_err[512];
+const char *sblas_last_error(void) { return g_err; }
+void sblas_set_error(const char *fmt, const char *a, const char *b, int line)
+{
+    snprintf(g_err, sizeof g_err, fmt, a, b, line);
+}
+
+#define CU(call)                                                                      \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) {                                                      \
+            sblas_set_error("%s failed: %s (sblas_plan.c:%d)", #call, cudaGetErrorString(e_), __LINE__); \
+            rc = 1;                                                                   \
+            goto fail;                                                                \
+        }                                                                             \
+    } while (0)
+
+/* ------------------------------------------------------------------ helpers */
+double sblas_get_time(void)          /* spmv/src/spmv_helper.cu:41-48: wall clock in seconds */
+{
+    struct timeval tv;
+    gettimeofday(&tv, NULL);
+    return (double)tv.tv_sec + (double)tv.tv_usec * 1e-6;
+}
+
+double sblas_get_gpu_availble_mem(int ngpu)   /* spmv_helper.cu:51-76: min free GB over GPUs */
+{
+    double best = 1e300;
+    for (int d = 0; d < ngpu; ++d) {
+        size_t fr = 0, tot = 0;
+        if (cudaSetDevice(d) != cudaSuccess || cudaMemGetInfo(&fr, &tot) != cudaSuccess) return 0.0;
+        const double gb = (double)fr / 1e9;
+        if (gb < best) best = gb;
+    }
+    return best;
+}
+
+/* last r in [0,m) with rp[r] <= idx: the row that really holds entry idx */
+static int true_row_of(int m, const long long *rp, long long idx)
+{
+    int lo = 0, hi = m;                       /* first r in [0,m] with rp[r] > idx */
+    while (lo < hi) {
+        const int mid = lo + (hi - lo) / 2;
+        if (rp[mid] <= idx) lo = mid + 1; else hi = mid;
+    }
+    return lo - 1 < 0 ? 0 : (lo - 1 >= m ? m - 1 : lo - 1);
+}
+
+static int env_int(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+/* `kernel` of the reference API -> kernel family + tile shape.
+ *   1: adaptive -- tile kernel (its per-tile reduction adapts to the rows inside the
+ *      tile) for anything big enough to fill the GPU, lanes-per-row kernel otherwise
+ *   2: nnz-balanced tile kernel everywhere (the reference's "merge-path" choice)
+ *   3: CSR5-style small tiles (1024 nnz) */
+static void pick_kernel(int kernel, long long dev_nnz, int *kind, int *ipt)
+{
+    *ipt = 16;
+    *kind = SBLAS_K_TILE;
+    if (kernel == 1 && dev_nnz < (long long)env_int("SBLAS_VEC_BELOW", 1 << 16)) *kind = SBLAS_K_VECTOR;
+    if (kernel == 3) *ipt = 4;
+    const char *k = getenv("SBLAS_KIND");
+    if (k && !strcmp(k, "vec")) *kind = SBLAS_K_VECTOR;
+    if (k && !strcmp(k, "tile")) *kind = SBLAS_K_TILE;
+    const int e = env_int("SBLAS_IPT", 0);
+    if (e == 4 || e == 8 || e == 16) *ipt = e;
+}
+
+/* ------------------------------------------------------------------ build */
+static void free_dev(sblas_dev *D)
+{
+    if (D->device >= 0) cudaSetDevice(D->device);
+    if (D->own_matrix) { cudaFree(D->d_val); cudaFree(D->d_col); }
+    cudaFree(D->d_rowptr); cudaFree(D->d_x); cudaFree(D->d_y);
+    if (D->edge_is_host) cudaFreeHost(D->h_edge_alloc); else if (!D->edge_bound) cudaFree(D->d_edge);
+    cudaFree(D->d_carry); cudaFree(D->d_tail); cudaFree(D->d_tstart);
+    cudaFree(D->d_mrow); cudaFree(D->d_mbeg); cudaFree(D->d_msrc);
+    if (D->streams) {
+        for (int c = 0; c < D->nstreams; ++c) {
+            if (D->streams[c]) cudaStreamDestroy(D->streams[c]);
+            if (D->ev_seg && D->ev_seg[c]) cudaEventDestroy(D->ev_seg[c]);
+        }
+    }
+    if (D->ev_in) cudaEventDestroy(D->ev_in);
+    if (D->ev_done) cudaEventDestroy(D->ev_done);
+    free(D->streams); free(D->ev_seg);
+    free(D->h_mrow); free(D->h_mbeg); free(D->h_msrc); free(D->h_msrc_off);
+}
+
+void sblas_spmv_plan_destroy(sblas_spmv_plan *P)
+{
+    if (!P) return;
+    for (int d = 0; d < P->ndev; ++d) free_dev(&P->devs[d]);
+    free(P->devs); free(P->segs); free(P->parts); free(P->g_owner); free(P->g_local);
+    free(P->g_lo); free(P->g_hi); free(P->g_sf); free(P->g_sl);
+    free(P);
+}
+
+/* Global segment table (every GPU / rank computes the same one): reference
+ * records + the rows each segment really covers + who shares what. */
+static int build_global(sblas_spmv_plan *P, const long long *rp)
+{
+    const int m = P->m;
+    int G = 0;
+    if (P->version == SBLAS_V2) {
+        G = sblas_v2_num_tasks(P->nnz, P->nb);
+    } else {
+        G = P->world;
+    }
+    if (G <= 0) return -1;
+    P->nparts = G;
+    P->parts = (sblas_part *)calloc((size_t)G, sizeof(sblas_part));
+    P->g_owner = (int *)calloc((size_t)G, sizeof(int));
+    P->g_local = (int *)calloc((size_t)G, sizeof(int));
+    P->g_lo = (int *)calloc((size_t)G, sizeof(int));
+    P->g_hi = (int *)calloc((size_t)G, sizeof(int));
+    P->g_sf = (int *)calloc((size_t)G, sizeof(int));
+    P->g_sl = (int *)calloc((size_t)G, sizeof(int));
+    if (!P->parts || !P->g_owner || !P->g_local || !P->g_lo || !P->g_hi || !P->g_sf || !P->g_sl) return -1;
+
+    if (P->version == SBLAS_BASELINE) sblas_partition_baseline(m, rp, G, P->parts);
+    else if (P->version == SBLAS_V1) sblas_partition_v1(m, P->nnz, rp, G, P->parts);
+    else sblas_generate_tasks_v2(m, P->nnz, rp, P->nb, P->parts);
+
+    int prev = -1;                 /* previous non-empty segment */
+    int prev_hi = -1;
+    for (int t = 0; t < G; ++t) {
+        sblas_part *p = &P->parts[t];
+        P->g_owner[t] = (P->version == SBLAS_V2) ? sblas_v2_task_owner(G, P->world, t) : t;
+        P->g_lo[t] = 0; P->g_hi[t] = -1; P->g_sf[t] = 0; P->g_sl[t] = 0;
+        if (P->version == SBLAS_BASELINE) {
+            P->g_lo[t] = p->start_row; P->g_hi[t] = p->end_row;       /* may be empty (dev_m == 0) */
+            continue;
+        }
+        if (p->end_idx < p->start_idx) continue;                       /* no nnz: nothing to run */
+        const int tsr = true_row_of(m, rp, p->start_idx);
+        const int ter = true_row_of(m, rp, p->end_idx);
+        const int split = p->start_idx > rp[tsr];
+        P->g_sf[t] = (prev >= 0) && split;
+        P->g_lo[t] = P->g_sf[t] ? tsr : prev_hi + 1;
+        P->g_hi[t] = ter;
+        if (prev >= 0) P->g_sl[prev] = P->g_sf[t];
+        prev = t; prev_hi = ter;
+    }
+    if (P->version != SBLAS_BASELINE) {
+        if (prev >= 0) {
+            P->g_hi[prev] = m - 1;                                     /* trailing empty rows */
+        } else {
+            /* matrix without entries: the first segment scales y */
+            P->g_lo[0] = 0; P->g_hi[0] = m - 1;
+            P->parts[0].start_idx = 0; P->parts[0].end_idx = -1;
+        }
+    }
+    return 0;
+}
+
+static int seg_is_live(const sblas_spmv_plan *P, int t) { return P->g_hi[t] >= P->g_lo[t]; }
+
+/* owner (global segment) of the row shared at the START of segment t: walk back */
+static int row_owner_seg(const sblas_spmv_plan *P, int t)
+{
+    int o = t;
+    while (P->g_sf[o]) {
+        int k = o - 1;
+        while (k >= 0 && !seg_is_live(P, k)) --k;
+        o = k;
+        /* o's last row is the shared row; if o is a single-row segment that is
+         * itself split at its start, keep walking */
+        if (!(P->g_sf[o] && P->g_lo[o] == P->g_hi[o])) break;
+    }
+    return o;
+}
+
+static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp, const int *col,
+                      const int *devices, int src_flags)
+{
+    int rc = 0;
+    long long *stage64 = NULL;
+    if (build_global(P, rp) != 0) { sblas_set_error("%s%s (line %d)", "partition failed", "", __LINE__); return -1; }
+
+    /* ---- local segments per GPU */
+    const int ndev = P->ndev;
+    int nloc = 0;
+    for (int t = 0; t < P->nparts; ++t) {
+        P->g_local[t] = -1;
+        if (!seg_is_live(P, t)) continue;
+        const int o = P->g_owner[t];
+        const int d = P->rank_mode ? (o == P->rank ? 0 : -1) : o;
+        if (d >= 0) ++nloc;
+    }
+    P->nseg = nloc;
+    P->segs = (sblas_seg *)calloc((size_t)(nloc > 0 ? nloc : 1), sizeof(sblas_seg));
+    for (int d = 0; d < ndev; ++d) { P->devs[d].seg_begin = -1; P->devs[d].seg_end = -1; }
+    int k = 0;
+    for (int t = 0; t < P->nparts; ++t) {
+        if (!seg_is_live(P, t)) continue;
+        const int o = P->g_owner[t];
+        const int d = P->rank_mode ? (o == P->rank ? 0 : -1) : o;
+        if (d < 0) continue;
+        sblas_seg *S = &P->segs[k];
+        S->gidx = t; S->dev = d;
+        sblas_dev *D = &P->devs[d];
+        if (D->seg_begin < 0) D->seg_begin = k;
+        D->seg_end = k + 1;
+        S->lidx = k - D->seg_begin;
+        P->g_local[t] = S->lidx;
+        ++k;
+    }
+    /* edge slot of a global segment = 2 * (index among its owner's live segments) */
+    {
+        int *cnt = (int *)calloc((size_t)P->world, sizeof(int));
+        P->max_local = 0;
+        for (int t = 0; t < P->nparts; ++t) {
+            if (!seg_is_live(P, t)) { P->g_local[t] = -1; continue; }
+            P->g_local[t] = cnt[P->g_owner[t]]++;
+            if (cnt[P->g_owner[t]] > P->max_local) P->max_local = cnt[P->g_owner[t]];
+        }
+        free(cnt);
+    }
+
+    /* ---- per GPU: resident range, buffers, upload */
+    for (int d = 0; d < ndev; ++d) {
+        sblas_dev *D = &P->devs[d];
+        D->device = devices[d];
+        if (D->seg_begin < 0) { D->rows = 0; D->nnz = 0; continue; }
+        const sblas_seg *S0 = &P->segs[D->seg_begin], *S1 = &P->segs[D->seg_end - 1];
+        D->first_idx = P->parts[S0->gidx].start_idx;
+        D->last_idx = P->parts[S1->gidx].end_idx;
+        for (int s = D->seg_begin; s < D->seg_end; ++s)           /* baseline blocks may be empty of nnz */
+            if (P->parts[P->segs[s].gidx].end_idx > D->last_idx) D->last_idx = P->parts[P->segs[s].gidx].end_idx;
+        D->first_row = P->g_lo[S0->gidx];
+        D->last_row = P->g_hi[S1->gidx];
+        D->rows = D->last_row - D->first_row + 1;
+        const long long dn = D->last_idx - D->first_idx + 1;
+        if (dn > 2147483647LL - 65536) {
+            sblas_set_error("%s%s (line %d)", "per-GPU nnz exceeds int32 (reference casts to int too)", "", __LINE__);
+            return -1;
+        }
+        D->nnz = (int)(dn < 0 ? 0 : dn);
+
+        CU(cudaSetDevice(D->device));
+        /* memory guard of the reference: shard > 0.8 x free -> -1
+         * (dspmv_mgpu_baseline.cu:70-79, dspmv_mgpu_v1.cu:106-116) */
+        {
+            size_t fr = 0, tot = 0;
+            CU(cudaMemGetInfo(&fr, &tot));
+            const double need = 12.0 * D->nnz * ((src_flags & SBLAS_SRC_DEVICE_SHARD) ? 0.0 : 1.0) +
+                                4.0 * (D->rows + 1) + 8.0 * P->n + 8.0 * D->rows;
+            if (need / 1e9 > 0.8 * ((double)fr / 1e9)) {
+                sblas_set_error("%s%s (line %d)", "shard exceeds 0.8 x free device memory", "", __LINE__);
+                rc = -1; goto fail;
+            }
+        }
+        D->nstreams = P->q > 1 ? P->q : 1;
+        D->streams = (cudaStream_t *)calloc((size_t)D->nstreams, sizeof(cudaStream_t));
+        D->ev_seg = (cudaEvent_t *)calloc((size_t)D->nstreams, sizeof(cudaEvent_t));
+        for (int c = 0; c < D->nstreams; ++c) {
+            CU(cudaStreamCreateWithFlags(&D->streams[c], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&D->ev_seg[c], cudaEventDisableTiming));
+        }
+        CU(cudaEventCreateWithFlags(&D->ev_in, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&D->ev_done, cudaEventDisableTiming));
+        cudaStream_t st = D->streams[0];
+
+        if (src_flags & SBLAS_SRC_DEVICE_SHARD) {
+            D->d_val = (double *)val; D->d_col = (int *)col; D->own_matrix = 0;
+        } else {
+            D->own_matrix = 1;
+            CU(cudaMalloc((void **)&D->d_val, (size_t)(D->nnz > 0 ? D->nnz : 1) * sizeof(double)));
+            CU(cudaMalloc((void **)&D->d_col, (size_t)(D->nnz > 0 ? D->nnz : 1) * sizeof(int)));
+            if (D->nnz > 0) {
+                CU(cudaMemcpyAsync(D->d_val, val + D->first_idx, (size_t)D->nnz * sizeof(double), cudaMemcpyHostToDevice, st));
+                CU(cudaMemcpyAsync(D->d_col, col + D->first_idx, (size_t)D->nnz * sizeof(int), cudaMemcpyHostToDevice, st));
+            }
+        }
+        CU(cudaMalloc((void **)&D->d_rowptr, (size_t)(D->rows + 1) * sizeof(int)));
+        CU(cudaMalloc((void **)&D->d_x, (size_t)(P->n > 0 ? P->n : 1) * sizeof(double)));
+        CU(cudaMalloc((void **)&D->d_y, (size_t)(D->rows > 0 ? D->rows : 1) * sizeof(double)));
+        /* int64 host row pointer slice -> int32 rebased/clamped, on the GPU */
+        CU(cudaMalloc((void **)&stage64, (size_t)(D->rows + 1) * sizeof(long long)));
+        CU(cudaMemcpyAsync(stage64, rp + D->first_row, (size_t)(D->rows + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+        CU(sblas_launch_rebase_rowptr(stage64, D->first_idx, D->nnz, (long long)D->rows + 1, D->d_rowptr, st));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaFree(stage64)); stage64 = NULL;
+
+        /* edge table: 2 doubles per local segment, device memory (peers read it over NVLink) */
+        const int nl = D->seg_end - D->seg_begin;
+        CU(cudaMalloc((void **)&D->d_edge, (size_t)(2 * (P->rank_mode ? P->max_local : nl) + 2) * sizeof(double)));
+        CU(cudaMemsetAsync(D->d_edge, 0, (size_t)(2 * (P->rank_mode ? P->max_local : nl) + 2) * sizeof(double), st));
+
+        /* ---- segments: kernel choice, tiles */
+        pick_kernel(P->kernel, D->nnz, &D->kind, &D->ipt);
+        const int TILE = sblas_tile_size(D->ipt);
+        long long tiles_total = 0;
+        for (int s = D->seg_begin; s < D->seg_end; ++s) {
+            sblas_seg *S = &P->segs[s];
+            const sblas_part *p = &P->parts[S->gidx];
+            sblas_seg_args *a = &S->args;
+            memset(a, 0, sizeof *a);
+            a->row_lo = P->g_lo[S->gidx] - D->first_row;
+            a->row_hi = P->g_hi[S->gidx] - D->first_row;
+            a->nz0 = (int)(p->start_idx - D->first_idx);
+            a->nz1 = (int)(p->end_idx + 1 - D->first_idx);
+            if (a->nz1 < a->nz0) a->nz1 = a->nz0;
+            a->skip_first = P->g_sf[S->gidx] ? a->row_lo : -1;
+            a->skip_last = P->g_sl[S->gidx] ? a->row_hi : -1;
+            a->tile0 = a->nz0 / TILE;
+            a->ntile = (a->nz1 > a->nz0) ? (int)(((long long)a->nz1 - 1) / TILE - a->tile0 + 1) : 0;
+            S->tile_off = tiles_total;
+            tiles_total += a->ntile + 1;
+            S->stream = S->lidx % D->nstreams;
+        }
+        if (D->kind == SBLAS_K_TILE) {
+            CU(cudaMalloc((void **)&D->d_tstart, (size_t)(tiles_total + 1) * sizeof(int)));
+            CU(cudaMalloc((void **)&D->d_carry, (size_t)(tiles_total + 1) * sizeof(double)));
+            CU(cudaMalloc((void **)&D->d_tail, (size_t)(tiles_total + 1) * sizeof(double)));
+        }
+        for (int s = D->seg_begin; s < D->seg_end; ++s) {
+            sblas_seg *S = &P->segs[s];
+            sblas_seg_args *a = &S->args;
+            a->val = D->d_val; a->col = D->d_col; a->rowptr = D->d_rowptr;
+            a->x = D->d_x; a->y = D->d_y;
+            a->edge = D->d_edge + 2 * S->lidx;
+            if (D->kind == SBLAS_K_TILE) {
+                a->tstart = D->d_tstart + S->tile_off;
+                a->carry = D->d_carry + S->tile_off;
+                a->tail = D->d_tail + S->tile_off;
+                if (a->ntile > 0) CU(sblas_launch_tile_rows(a, TILE, D->d_tstart + S->tile_off, st));
+            }
+        }
+        CU(cudaStreamSynchronize(st));
+    }
+
+    /* ---- peer access between the GPUs of an in-process plan */
+    P->p2p = 0;
+    if (!P->rank_mode && ndev > 1) {
+        P->p2p = 1;
+        for (int a = 0; a < ndev && P->p2p; ++a)
+            for (int b = 0; b < ndev; ++b) {
+                if (a == b) continue;
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, P->devs[a].device, P->devs[b].device);
+                if (!can) { P->p2p = 0; break; }
+            }
+        if (P->p2p) {
+            for (int a = 0; a < ndev; ++a) {
+                cudaSetDevice(P->devs[a].device);
+                for (int b = 0; b < ndev; ++b) {
+                    if (a == b) continue;
+                    cudaError_t e = cudaDeviceEnablePeerAccess(P->devs[b].device, 0);
+                    if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                    else if (e != cudaSuccess) { cudaGetLastError(); P->p2p = 0; }
+                }
+            }
+        }
+        if (!P->p2p) {
+            sblas_set_error("%s%s (line %d)", "multi-GPU plan needs peer access between all GPUs (NVLink/NVSwitch)", "", __LINE__);
+            rc = 1; goto fail;
+        }
+    }
+
+    /* ---- merge lists: one entry per split row, on the GPU that owns the row's start.
+     * Sources are listed in ascending global segment order (deterministic sum). */
+    for (int d = 0; d < ndev; ++d) {
+        sblas_dev *D = &P->devs[d];
+        if (D->seg_begin < 0) continue;
+        int nrow = 0, nsrc = 0;
+        /* first pass counts, second pass fills */
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1) {
+                D->h_mrow = (int *)calloc((size_t)nrow + 1, sizeof(int));
+                D->h_mbeg = (int *)calloc((size_t)nrow + 2, sizeof(int));
+                D->h_msrc = (const double **)calloc((size_t)nsrc + 1, sizeof(double *));
+                D->h_msrc_off = (long long *)calloc((size_t)nsrc + 1, sizeof(long long));
+                nrow = 0; nsrc = 0;
+            }
+            for (int t = 0; t < P->nparts; ++t) {
+                if (!seg_is_live(P, t) || !P->g_sl[t]) continue;
+                /* t's last row is split with t+1...; only start a list where the row STARTS */
+                if (P->g_sf[t] && P->g_lo[t] == P->g_hi[t]) continue;          /* middle of a longer chain */
+                const int od = P->rank_mode ? (P->g_owner[t] == P->rank ? 0 : -1) : P->g_owner[t];
+                if (od != d) continue;
+                if (pass == 1) { D->h_mrow[nrow] = P->g_hi[t] - D->first_row; D->h_mbeg[nrow] = nsrc; }
+                /* chain: t (edge[1]), then following live segments while they are split at their start */
+                int u = t, which = 1;
+                for (;;) {
+                    if (pass == 1) {
+                        const long long off = 2LL * P->g_local[u] + which;
+                        D->h_msrc_off[nsrc] = (long long)P->g_owner[u] * (2LL * P->max_local) + off;
+                        if (!P->rank_mode) D->h_msrc[nsrc] = P->devs[P->g_owner[u]].d_edge + off;
+                    }
+                    ++nsrc;
+                    /* next contributor */
+                    int v = u + 1;
+                    while (v < P->nparts && !seg_is_live(P, v)) ++v;
+                    if (v >= P->nparts || !P->g_sf[v]) break;
+                    const int cont = (which == 1) ? P->g_sl[u] : (P->g_lo[u] == P->g_hi[u] && P->g_sl[u]);
+                    if (!cont) break;
+                    u = v; which = 0;
+                }
+                ++nrow;
+            }
+        }
+        D->nmerge = nrow; D->nmsrc = nsrc;
+        D->h_mbeg[nrow] = nsrc;
+        if (nrow > 0) {
+            CU(cudaSetDevice(D->device));
+            CU(cudaMalloc((void **)&D->d_mrow, (size_t)nrow * sizeof(int)));
+            CU(cudaMalloc((void **)&D->d_mbeg, (size_t)(nrow + 1) * sizeof(int)));
+            CU(cudaMalloc((void **)&D->d_msrc, (size_t)nsrc * sizeof(double *)));
+            CU(cudaMemcpy(D->d_mrow, D->h_mrow, (size_t)nrow * sizeof(int), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(D->d_mbeg, D->h_mbeg, (size_t)(nrow + 1) * sizeof(int), cudaMemcpyHostToDevice));
+            if (!P->rank_mode)
+                CU(cudaMemcpy(D->d_msrc, D->h_msrc, (size_t)nsrc * sizeof(double *), cudaMemcpyHostToDevice));
+        }
+    }
+    return 0;
+fail:
+    if (stage64) cudaFree(stage64);
+    return rc;
+}
+
+static int plan_alloc(sblas_spmv_plan **out, int version, int m, int n, long long nnz, int world, int ndev,
+                      int kernel, long long nb, int q)
+{
+    if (!out || m <= 0 || n <= 0 || nnz < 0 || world <= 0) {
+        sblas_set_error("%s%s (line %d)", "invalid argument", "", __LINE__);
+        return -1;
+    }
+    if (kernel != 1 && kernel != 2 && kernel != 3) {
+        sblas_set_error("%s%s (line %d)", "kernel must be 1, 2 or 3", "", __LINE__);
+        return -1;
+    }
+    sblas_spmv_plan *P = (sblas_spmv_plan *)calloc(1, sizeof *P);
+    if (!P) return 1;
+    P->version = version; P->m = m; P->n = n; P->nnz = nnz; P->world = world; P->ndev = ndev;
+    P->kernel = kernel; P->nb = nb; P->q = q > 0 ? q : 1;
+    P->devs = (sblas_dev *)calloc((size_t)ndev, sizeof(sblas_dev));
+    for (int d = 0; d < ndev; ++d) P->devs[d].device = -1;
+    *out = P;
+    return 0;
+}
+
+/* v2's nb clamp and argument check, dspmv_mgpu_v2.cu:43-46 */
+static int v2_clamp(long long *nb, int ngpu, int q)
+{
+    if (ngpu <= 0 || q <= 0) return -1;
+    const double free_gb = sblas_get_gpu_availble_mem(ngpu);
+    const long long cap = (long long)(0.8 * free_gb * 1e9 / 16.0) / q;
+    if (*nb > cap) *nb = cap;
+    return (*nb <= 0) ? -1 : 0;
+}
+
+int sblas_spmv_plan_create(sblas_spmv_plan **plan, int version, int m, int n, long long nnz,
+                           const double *csrVal, const long long *csrRowPtr, const int *csrColIndex,
+                           int ngpu, int kernel, long long nb, int q)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count < ngpu || ngpu <= 0) {
+        cudaGetLastError();
+        sblas_set_error("%s%s (line %d)", "not enough CUDA devices (no CPU fallback)", "", __LINE__);
+        return (version == SBLAS_V2) ? -1 : 1;
+    }
+    if (version == SBLAS_V2 && v2_clamp(&nb, ngpu, q) != 0) return -1;
+    int rc = plan_alloc(plan, version, m, n, nnz, ngpu, ngpu, kernel, nb, version == SBLAS_V2 ? q : 1);
+    if (rc) return rc;
+    int devices[64];
+    if (ngpu > 64) { sblas_spmv_plan_destroy(*plan); *plan = NULL; return -1; }
+    for (int d = 0; d < ngpu; ++d) devices[d] = d;
+    (*plan)->rank_mode = 0;
+    rc = plan_build(*plan, csrVal, csrRowPtr, csrColIndex, devices, SBLAS_SRC_HOST);
+    if (rc) { sblas_spmv_plan_destroy(*plan); *plan = NULL; }
+    return rc;
+}
+
+int sblas_spmv_plan_create_rank(sblas_spmv_plan **plan, int version, int m, int n, long long nnz,
+                                const double *csrVal, const long long *csrRowPtr, const int *csrColIndex,
+                                int world, int rank, int device, int kernel, long long nb, int q, int flags)
+{
+    if (rank < 0 || rank >= world) return -1;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        cudaGetLastError();
+        sblas_set_error("%s%s (line %d)", "cudaSetDevice failed (no CPU fallback)", "", __LINE__);
+        return 1;
+    }
+    if (version == SBLAS_V2 && (nb <= 0 || q <= 0)) return -1;
+    int rc = plan_alloc(plan, version, m, n, nnz, world, 1, kernel, nb, version == SBLAS_V2 ? q : 1);
+    if (rc) return rc;
+    (*plan)->rank_mode = 1; (*plan)->rank = rank;
+    rc = plan_build(*plan, csrVal, csrRowPtr, csrColIndex, &device, flags);
+    if (rc) { sblas_spmv_plan_destroy(*plan); *plan = NULL; }
+    return rc;
+}
+
+/* ------------------------------------------------------------------ execute */
+static int enqueue_segments(sblas_spmv_plan *P, int d, double alpha, double beta)
+{
+    int rc = 0;
+    sblas_dev *D = &P->devs[d];
+    if (D->seg_begin < 0) return 0;
+    CU(cudaSetDevice(D->device));
+    if (D->nstreams > 1) {
+        CU(cudaEventRecord(D->ev_in, D->streams[0]));
+        for (int c = 1; c < D->nstreams; ++c) CU(cudaStreamWaitEvent(D->streams[c], D->ev_in, 0));
+    }
+    for (int s = D->seg_begin; s < D->seg_end; ++s) {
+        sblas_seg *S = &P->segs[s];
+        S->args.alpha = alpha; S->args.beta = beta;
+        CU(sblas_launch_spmv_segment(&S->args, D->kind, D->ipt, 0, D->streams[S->stream]));
+    }
+    for (int c = 1; c < D->nstreams; ++c) {
+        CU(cudaEventRecord(D->ev_seg[c], D->streams[c]));
+        CU(cudaStreamWaitEvent(D->streams[0], D->ev_seg[c], 0));
+    }
+    CU(cudaEventRecord(D->ev_done, D->streams[0]));
+fail:
+    return rc;
+}
+
+static int enqueue_merge(sblas_spmv_plan *P, int d, double alpha, double beta)
+{
+    int rc = 0;
+    sblas_dev *D = &P->devs[d];
+    if (D->seg_begin < 0 || D->nmerge == 0) return 0;
+    CU(cudaSetDevice(D->device));
+    /* wait for every GPU that contributes a partial sum (cross-device event wait) */
+    if (!P->rank_mode)
+        for (int o = 0; o < P->ndev; ++o)
+            if (o != d && P->devs[o].seg_begin >= 0) CU(cudaStreamWaitEvent(D->streams[0], P->devs[o].ev_done, 0));
+    CU(sblas_launch_edge_merge(D->d_mrow, D->d_mbeg, (const double *const *)D->d_msrc, D->nmerge, D->d_y,
+                               alpha, beta, D->streams[0]));
+fail:
+    return rc;
+}
+
+int sblas_spmv_plan_execute_device(sblas_spmv_plan *P, double alpha, double beta, int sync)
+{
+    int rc = 0;
+    for (int d = 0; d < P->ndev; ++d) if ((rc = enqueue_segments(P, d, alpha, beta)) != 0) return rc;
+    if (!P->rank_mode)
+        for (int d = 0; d < P->ndev; ++d) if ((rc = enqueue_merge(P, d, alpha, beta)) != 0) return rc;
+    if (sync) {
+        for (int d = 0; d < P->ndev; ++d) {
+            if (P->devs[d].seg_begin < 0) continue;
+            CU(cudaSetDevice(P->devs[d].device));
+            CU(cudaStreamSynchronize(P->devs[d].streams[0]));
+        }
+    }
+fail:
+    return rc;
+}
+
+/* rank plans: finish the split rows this rank owns from a table that holds every
+ * rank's edge partials (world x 2*max_local doubles, rank-major; e.g. the output
+ * of an NCCL all-gather of each rank's edge table, or a symmetric-memory buffer) */
+int sblas_spmv_plan_merge_gathered(sblas_spmv_plan *P, const double *gathered, double alpha, double beta)
+{
+    int rc = 0;
+    sblas_dev *D = &P->devs[0];
+    if (!P->rank_mode || D->seg_begin < 0 || D->nmerge == 0) return 0;
+    CU(cudaSetDevice(D->device));
+    if (gathered != P->gather_base) {
+        for (int i = 0; i < D->nmsrc; ++i) D->h_msrc[i] = gathered + D->h_msrc_off[i];
+        CU(cudaMemcpyAsync(D->d_msrc, D->h_msrc, (size_t)D->nmsrc * sizeof(double *), cudaMemcpyHostToDevice, D->streams[0]));
+        CU(cudaStreamSynchronize(D->streams[0]));
+        P->gather_base = gathered;
+    }
+    CU(sblas_launch_edge_merge(D->d_mrow, D->d_mbeg, (const double *const *)D->d_msrc, D->nmerge, D->d_y,
+                               alpha, beta, D->streams[0]));
+fail:
+    return rc;
+}
+
+int sblas_spmv_plan_execute(sblas_spmv_plan *P, const double *alpha, const double *x, const double *beta, double *y)
+{
+    int rc = 0;
+    const double al = *alpha, be = *beta;
+    const int nd = P->ndev;
+    /* ---- x: every GPU uploads its 1/nd slice over its own PCIe link, then the slices
+     * are exchanged over NVLink (replaces nd full-size H2D copies, dspmv_mgpu_v1.cu:183) */
+    int live = 0;
+    for (int d = 0; d < nd; ++d) if (P->devs[d].seg_begin >= 0) ++live;
+    int li = 0;
+    for (int d = 0; d < nd; ++d) {
+        sblas_dev *D = &P->devs[d];
+        if (D->seg_begin < 0) continue;
+        CU(cudaSetDevice(D->device));
+        cudaStream_t st = D->streams[0];
+        const long long lo = (long long)P->n * li / live, hi = (long long)P->n * (li + 1) / live;
+        D->xs_lo = lo; D->xs_hi = hi;
+        if (hi > lo) CU(cudaMemcpyAsync(D->d_x + lo, x + lo, (size_t)(hi - lo) * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (be != 0.0)
+            CU(cudaMemcpyAsync(D->d_y, y + D->first_row, (size_t)D->rows * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(D->ev_in, st));
+        ++li;
+    }
+    if (live > 1) {
+        for (int d = 0; d < nd; ++d) {
+            sblas_dev *D = &P->devs[d];
+            if (D->seg_begin < 0) continue;
+            CU(cudaSetDevice(D->device));
+            for (int o = 0; o < nd; ++o) {
+                sblas_dev *O = &P->devs[o];
+                if (o == d || O->seg_begin < 0 || O->xs_hi <= O->xs_lo) continue;
+                /* pull O's slice once it has landed there */
+                CU(cudaStreamWaitEvent(D->streams[0], O->ev_in, 0));
+                CU(cudaMemcpyPeerAsync(D->d_x + O->xs_lo, D->device, O->d_x + O->xs_lo, O->device,
+                                       (size_t)(O->xs_hi - O->xs_lo) * sizeof(double), D->streams[0]));
+            }
+        }
+    }
+    if ((rc = sblas_spmv_plan_execute_device(P, al, be, 0)) != 0) return rc;
+    /* ---- y: every GPU downloads the rows it owns (disjoint host ranges) */
+    for (int d = 0; d < nd; ++d) {
+        sblas_dev *D = &P->devs[d];
+        if (D->seg_begin < 0) continue;
+        CU(cudaSetDevice(D->device));
+        const sblas_seg *S0 = &P->segs[D->seg_begin];
+        int skip = 0;
+        if (P->g_sf[S0->gidx]) {
+            const int og = row_owner_seg(P, S0->gidx);
+            const int od = P->rank_mode ? (P->g_owner[og] == P->rank ? 0 : -1) : P->g_owner[og];
+            if (od != d) skip = 1;
+        }
+        if (D->rows - skip > 0)
+            CU(cudaMemcpyAsync(y + D->first_row + skip, D->d_y + skip, (size_t)(D->rows - skip) * sizeof(double),
+                               cudaMemcpyDeviceToHost, D->streams[0]));
+    }
+    for (int d = 0; d < nd; ++d) {
+        sblas_dev *D = &P->devs[d];
+        if (D->seg_begin < 0) continue;
+        CU(cudaSetDevice(D->device));
+        CU(cudaStreamSynchronize(D->streams[0]));
+    }
+fail:
+    return rc;
+}
+
+/* ------------------------------------------------------------------ accessors */
+int sblas_spmv_plan_num_devices(const sblas_spmv_plan *P) { return P->ndev; }
+int sblas_spmv_plan_num_segments(const sblas_spmv_plan *P) { return P->nparts; }
+int sblas_spmv_plan_segment(const sblas_spmv_plan *P, int seg, sblas_part *out, int *device)
+{
+    if (seg < 0 || seg >= P->nparts) return -1;
+    if (out) *out = P->parts[seg];
+    if (device) *device = P->g_owner[seg];
+    return 0;
+}
+double *sblas_spmv_plan_x(sblas_spmv_plan *P, int dev) { return P->devs[dev].d_x; }
+double *sblas_spmv_plan_y(sblas_spmv_plan *P, int dev, int *first_row, int *rows)
+{
+    if (first_row) *first_row = P->devs[dev].first_row;
+    if (rows) *rows = P->devs[dev].rows;
+    return P->devs[dev].d_y;
+}
+const int *sblas_spmv_plan_rowptr(sblas_spmv_plan *P, int dev, int *count)
+{
+    if (count) *count = P->devs[dev].rows + 1;
+    return P->devs[dev].d_rowptr;
+}
+void *sblas_spmv_plan_stream(sblas_spmv_plan *P, int dev) { return P->devs[dev].streams ? (void *)P->devs[dev].streams[0] : NULL; }
+double *sblas_spmv_plan_edge_ptr(sblas_spmv_plan *P, int dev) { return P->devs[dev].d_edge; }
+int sblas_spmv_plan_edge_slots(const sblas_spmv_plan *P) { return 2 * P->max_local; }
+
+int sblas_spmv_plan_bind_edge_table(sblas_spmv_plan *P, double *device_block)
+{
+    if (!P->rank_mode || !device_block) return -1;
+    sblas_dev *D = &P->devs[0];
+    if (D->seg_begin < 0) return 0;
+    cudaSetDevice(D->device);
+    if (!D->edge_is_host && !D->edge_bound) cudaFree(D->d_edge);
+    D->d_edge = device_block;
+    D->edge_bound = 1;
+    for (int s = D->seg_begin; s < D->seg_end; ++s) P->segs[s].args.edge = D->d_edge + 2 * P->segs[s].lidx;
+    return 0;
+}
+
+int sblas_memcpy(void *dst, const void *src, unsigned long long bytes, int kind)
+{
+    return (int)cudaMemcpy(dst, src, (size_t)bytes, (enum cudaMemcpyKind)kind);
+}
+int sblas_device_synchronize(void) { return (int)cudaDeviceSynchronize(); }
+
+int sblas_spmv_plan_edges(sblas_spmv_plan *P, double *out)
+{
+    int rc = 0;
+    for (int t = 0; t < P->nparts; ++t) { out[2 * t] = 0.0; out[2 * t + 1] = 0.0; }
+    for (int s = 0; s < P->nseg; ++s) {
+        sblas_seg *S = &P->segs[s];
+        sblas_dev *D = &P->devs[S->dev];
+        CU(cudaSetDevice(D->device));
+        CU(cudaMemcpy(out + 2 * S->gidx, D->d_edge + 2 * S->lidx, 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+fail:
+    return rc;
+}
+
+double sblas_spmv_plan_alg_bytes(const sblas_spmv_plan *P, int beta_nonzero, long long x_touched_per_gpu)
+{
+    double b = 0.0;
+    for (int d = 0; d < P->ndev; ++d) {
+        const sblas_dev *D = &P->devs[d];
+        if (D->seg_begin < 0) continue;
+        const double xt = x_touched_per_gpu >= 0 ? (double)x_touched_per_gpu : (double)P->n;
+        b += 12.0 * D->nnz + 4.0 * (D->rows + 1) + 8.0 * xt + 8.0 * D->rows * (beta_nonzero ? 2.0 : 1.0);
+    }
+    return b;
+}
+
+int sblas_spmv_plan_launches(const sblas_spmv_plan *P)
+{
+    int n = 0;
+    for (int s = 0; s < P->nseg; ++s) {
+        const sblas_dev *D = &P->devs[P->segs[s].dev];
+        const sblas_seg_args *a = &P->segs[s].args;
+        if (a->row_hi < a->row_lo) continue;
+        n += (D->kind == SBLAS_K_TILE && a->ntile > 0) ? 2 : 1;
+    }
+    for (int d = 0; d < P->ndev; ++d) if (P->devs[d].nmerge > 0) ++n;
+    return n;
+}

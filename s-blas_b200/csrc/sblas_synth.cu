@@ -1,0 +1,95 @@
+/* sblas_synth.cu -- synthetic CSR content on the GPU (see include/sblas_synth.h). */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "sblas_synth.h"
+
+namespace {
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z)          /* splitmix64 finaliser */
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ double u01(uint64_t h) { return ((h >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+
+/* sorted-unique column j of `len` inside the window [start, start+W), W >= len */
+__device__ __forceinline__ int strat_col(long long start, long long W, long long len, long long j, uint64_t h)
+{
+    const long long lo = (long long)(((__int128)j * W) / len);
+    const long long hi = (long long)(((__int128)(j + 1) * W) / len);
+    const long long span = hi - lo > 0 ? hi - lo : 1;
+    return (int)(start + lo + (long long)(h % (uint64_t)span));
+}
+
+__global__ void fill_csr_kernel(const long long *__restrict__ rp, int row_first, int nrows, long long k0,
+                                long long k1, int n, int mode, long long band, uint64_t seed, int vmode,
+                                double vconst, double *__restrict__ val, int *__restrict__ col)
+{
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = warp; i < nrows; i += nwarps) {
+        const long long b = rp[i], e = rp[i + 1];
+        if (e <= k0 || b >= k1) continue;
+        const long long len = e - b;
+        const long long row = (long long)row_first + i;
+        int m = mode;
+        if (m == SBLAS_COLS_CIRCUIT) {
+            const bool hub = (mix64(seed ^ (uint64_t)row * 0x51ull) % 5u) == 0u;
+            m = (hub || len > 2 * band) ? SBLAS_COLS_UNIFORM : SBLAS_COLS_BANDED;
+        }
+        long long W = n, start = 0;
+        if (m == SBLAS_COLS_BANDED) {
+            W = 2 * band < n ? 2 * band : n;
+            if (W < len) W = len < n ? len : n;
+            start = row - W / 2;
+            if (start < 0) start = 0;
+            if (start + W > n) start = n - W;
+        }
+        const long long jb = (b > k0 ? b : k0) - b, je = (e < k1 ? e : k1) - b;
+        for (long long j = jb + lane; j < je; j += 32) {
+            const long long k = b + j;
+            const uint64_t h = mix64(seed ^ (uint64_t)k);
+            int c;
+            if (m == SBLAS_COLS_PREFIX) c = (int)(j < n ? j : n - 1);
+            else if (len <= W) c = strat_col(start, W, len, j, h);
+            else c = (int)(j % n);
+            col[k - k0] = c;
+            val[k - k0] = vmode ? vconst : u01(mix64(h));
+        }
+    }
+}
+
+__global__ void fill_uniform_kernel(double *p, long long count, uint64_t seed, double lo, double hi)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < count; i += stride) p[i] = lo + (hi - lo) * u01(mix64(seed ^ (uint64_t)i * 0x2545F4914F6CDD1Dull));
+}
+
+}  // namespace
+
+extern "C" int sblas_synth_fill_csr(const long long *d_rowptr, int row_first, int nrows, long long k0, long long k1,
+                                    int n, int cols_mode, long long band, unsigned long long seed, int value_mode,
+                                    double value_const, double *d_val, int *d_col, void *stream)
+{
+    if (nrows <= 0 || k1 <= k0) return 0;
+    long long blocks = ((long long)nrows * 32 + 255) / 256;
+    if (blocks > 148LL * 64) blocks = 148LL * 64;
+    fill_csr_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_rowptr, row_first, nrows, k0, k1, n,
+                                                                         cols_mode, band, seed, value_mode,
+                                                                         value_const, d_val, d_col);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int sblas_synth_fill_uniform(double *d_p, long long count, unsigned long long seed, double lo, double hi,
+                                        void *stream)
+{
+    if (count <= 0) return 0;
+    long long blocks = (count + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    fill_uniform_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_p, count, seed, lo, hi);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,95 @@
+"""Host logic of the product (C, via the C-ABI): the three partitioners must be bit-exact
+with the oracle / the reference's golden vectors.  CPU only -- no compute calls."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import sblas_b200 as sb
+from conftest import GOLDEN
+
+KEYS = ("start_idx", "end_idx", "start_row", "end_row", "start_flag", "end_flag", "dev_m", "dev_nnz")
+
+
+def _rowptrs():
+    rng = np.random.default_rng(99)
+    out = []
+    for t in range(25):
+        m = int(rng.integers(1, 500))
+        cnt = rng.integers(1, 10, size=m)
+        if t % 5 == 0:
+            cnt[rng.integers(0, m)] = int(rng.integers(100, 2000))       # a row spanning several shards
+        rp = np.zeros(m + 1, np.int64)
+        rp[1:] = np.cumsum(cnt)
+        out.append(rp)
+    return out
+
+
+def test_get_row_from_index_bit_exact():
+    g = np.load(os.path.join(GOLDEN, "ref_row_from_index.npz"))
+    for i in range(40):
+        rp, ans = g["rp%d" % i], g["ans%d" % i]
+        got = [sb.get_row_from_index(len(rp) - 1, rp, k) for k in range(len(ans))]
+        assert got == ans.tolist()
+
+
+def test_v1_partition_bit_exact(qh768):
+    for rp in [qh768["rowptr"]] + _rowptrs():
+        for ngpu in (1, 2, 3, 4, 8):
+            if ngpu > rp[-1]:
+                continue
+            a, b = sb.partition_v1(rp, ngpu), oracle.partition_v1(rp, ngpu)
+            for k in KEYS:
+                assert (a[k] == b[k]).all(), (k, ngpu)
+
+
+def test_v2_tasks_bit_exact(qh768):
+    for rp in [qh768["rowptr"]] + _rowptrs()[:10]:
+        nnz = int(rp[-1])
+        for d in (1, 2, 4, 8):
+            for c in (1, 2, 4, 8):
+                nb = nnz // (d * c)                 # the harness sweep, dspmv_test.cu:314-332
+                if nb <= 0:
+                    continue
+                a, b = sb.generate_tasks_v2(rp, nb), oracle.generate_tasks_v2(rp, nb)
+                for k in KEYS:
+                    assert (a[k] == b[k]).all(), (k, nb)
+                T = len(a["dev_m"])
+                # fixed task->GPU map honours the reference quota (dspmv_mgpu_v2.cu:125-126)
+                owners = [sb.v2_task_owner(T, d, t) for t in range(T)]
+                assert owners == sorted(owners)
+                for g in range(d):
+                    assert owners.count(g) == oracle.lib().oracle_v2_quota(T, g, d)
+
+
+def test_baseline_partition_bit_exact(qh768):
+    for rp in [qh768["rowptr"]] + _rowptrs():
+        for ngpu in (1, 2, 3, 4, 8):
+            a, b = sb.partition_baseline(rp, ngpu), oracle.partition_baseline(rp, ngpu)
+            for k in ("start_row", "end_row", "dev_m", "dev_nnz"):
+                assert (a[k] == b[k]).all(), (k, ngpu)
+
+
+def test_local_rowptr_bit_exact(qh768):
+    rp = qh768["rowptr"]
+    for ngpu in (2, 4, 8):
+        p = sb.partition_v1(rp, ngpu)
+        for d in range(ngpu):
+            part = {k: p[k][d] for k in KEYS}
+            want = oracle.local_rowptr_v1(rp, part["start_idx"], part["start_row"], part["dev_m"], part["dev_nnz"])
+            assert (sb.local_rowptr(rp, part) == want).all()
+        b = sb.partition_baseline(rp, ngpu)
+        for d in range(ngpu):
+            part = {k: b[k][d] for k in KEYS}
+            want = oracle.local_rowptr_baseline(rp, part["start_row"], part["dev_m"])
+            assert (sb.local_rowptr(rp, part, baseline=True) == want).all()
+
+
+def test_golden_known_answers(qh768):
+    gold = json.load(open(os.path.join(GOLDEN, "ref_partitions.json")))
+    for g, rows in gold["qh768"]["v1_known_answers_survey_8c"].items():
+        p = sb.partition_v1(qh768["rowptr"], int(g))
+        got = [[int(p[k][i]) for k in KEYS[:6]] for i in range(int(g))]
+        assert got == rows

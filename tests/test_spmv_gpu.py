@@ -1,0 +1,156 @@
+"""Parity of the CUDA path with the oracle, through the C-ABI (ctypes on
+libsblas_spmv.so).  Tolerance (BASELINE.json north_star): per row
+|y_gpu - y_oracle| <= 1e-12 * (|alpha| sum_j |a_ij||x_j| + |beta||y_i|).
+Run with `-m gpu` on a B200."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import sblas_b200 as sb
+from conftest import check_tol, make_csr
+
+pytestmark = pytest.mark.gpu
+A, B = 0.8401877171547095, 0.39438292681909304        # the harness's ALPHA/BETA in f mode
+
+
+def ngpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def run_all_versions(rp, col, val, x, alpha, beta, y0, ngpu_list=(1,), kernels=(1, 2, 3), what=""):
+    m, n, nnz = len(rp) - 1, len(x), int(rp[-1])
+    want = oracle.csr_spmv(rp, col, val, x, alpha, beta, y0)
+    bound = oracle.csr_spmv_bound(rp, col, val, x, alpha, beta, y0)
+    for g in ngpu_list:
+        y = y0.copy()
+        assert sb.spMV_mgpu_baseline(m, n, nnz, alpha, val, rp, col, x, beta, y, g) == 0, sb.last_error()
+        check_tol(y, want, bound, "%s baseline ngpu=%d" % (what, g))
+        for k in kernels:
+            y = y0.copy()
+            assert sb.spMV_mgpu_v1(m, n, nnz, alpha, val, rp, col, x, beta, y, g, k) == 0, sb.last_error()
+            check_tol(y, want, bound, "%s v1 ngpu=%d kernel=%d" % (what, g, k))
+            for c in (1, 2, 8):
+                nb = nnz // (g * c)
+                if nb <= 0:
+                    continue
+                y = y0.copy()
+                assert sb.spMV_mgpu_v2(m, n, nnz, alpha, val, rp, col, x, beta, y, g, k, nb, c) == 0, sb.last_error()
+                check_tol(y, want, bound, "%s v2 ngpu=%d kernel=%d nb=%d q=%d" % (what, g, k, nb, c))
+    return want
+
+
+def gpu_counts():
+    return [g for g in (1, 2, 4, 8) if g <= ngpus()]
+
+
+def test_qh768_harness_conditions(qh768):
+    """Config 1: sample matrix as the harness loads it, x = 1, y = 0, harness alpha/beta."""
+    x = np.ones(qh768["n"])
+    run_all_versions(qh768["rowptr"], qh768["col"], qh768["val"], x, A, B, np.zeros(qh768["m"]),
+                     gpu_counts(), what="qh768")
+
+
+def test_qh768_nonzero_y_and_beta(qh768):
+    """What the reference never tests: y != 0, beta != 0 through the split-row merge."""
+    rng = np.random.default_rng(1)
+    x = rng.uniform(0.5, 1.5, qh768["n"])
+    y0 = rng.standard_normal(qh768["m"]) * 1e9
+    run_all_versions(qh768["rowptr"], qh768["col"], qh768["val"], x, A, B, y0, gpu_counts(), what="qh768 y!=0")
+
+
+def test_generator_g200_and_g10000():
+    """INSTALL.md smoke input `g 200` and a batch_test.sh-size input, harness vectors."""
+    for n in (200, 10000):
+        r, c, v, alpha, beta = oracle.gen_g(n)
+        rp = oracle.coo_to_rowptr(n, r)
+        run_all_versions(rp, c, v, np.ones(n), alpha, beta, np.zeros(n), gpu_counts(),
+                         kernels=(1, 2) if n > 200 else (1, 2, 3), what="g %d" % n)
+
+
+@pytest.mark.parametrize("kind", ["vec", "tile"])
+@pytest.mark.parametrize("ipt", [4, 8, 16])
+def test_random_shapes_each_kernel_family(kind, ipt, monkeypatch):
+    """Short rows, empty rows, long rows, rows much longer than a tile, unsorted/duplicate columns."""
+    monkeypatch.setenv("SBLAS_KIND", kind)
+    monkeypatch.setenv("SBLAS_IPT", str(ipt))
+    rng = np.random.default_rng(ipt)
+    shapes = {
+        "short": rng.integers(1, 9, size=5000),
+        "with_empty": rng.integers(0, 4, size=7000),
+        "mixed": np.concatenate([rng.integers(0, 6, size=3000), [20000, 1, 0, 0, 9000], rng.integers(50, 300, size=200)]),
+        "power_law": np.minimum((rng.pareto(1.2, size=4000) * 3).astype(np.int64) + 1, 60000),
+        "all_long": rng.integers(2000, 9000, size=40),
+        "many_empty_then_one": np.concatenate([np.zeros(10000, np.int64), [5], np.zeros(9000, np.int64)]),
+        "leading_trailing_empty": np.concatenate([[0, 0, 0], rng.integers(1, 50, size=500), [0, 0]]),
+    }
+    for name, lens in shapes.items():
+        m, n = len(lens), 4099
+        rp, col, val = make_csr(rng, m, n, lens, sort_cols=(name != "mixed"))
+        x, y0 = rng.standard_normal(n), rng.standard_normal(m)
+        run_all_versions(rp, col, val, x, -1.75, 0.625, y0, (1,), kernels=(1,), what="%s/%s/%d" % (name, kind, ipt))
+        run_all_versions(rp, col, val, x, 2.0, 0.0, y0, (1,), kernels=(1,), what="%s/%s/%d beta=0" % (name, kind, ipt))
+
+
+def test_row_spanning_many_segments():
+    """A row longer than nnz/ngpu (v1) and than nb (v2): >= 3 segments share it."""
+    rng = np.random.default_rng(17)
+    lens = np.array([3, 1, 100000, 2, 2, 70000, 1], np.int64)
+    rp, col, val = make_csr(rng, len(lens), 5000, lens)
+    x, y0 = rng.uniform(0.1, 1.0, 5000), rng.standard_normal(len(lens))
+    m, n, nnz = len(lens), 5000, int(rp[-1])
+    want = oracle.csr_spmv(rp, col, val, x, A, B, y0)
+    bound = oracle.csr_spmv_bound(rp, col, val, x, A, B, y0)
+    for nb in (1000, 4096, 30000, 170010):
+        for q in (1, 4):
+            y = y0.copy()
+            assert sb.spMV_mgpu_v2(m, n, nnz, A, val, rp, col, x, B, y, 1, 2, nb, q) == 0, sb.last_error()
+            check_tol(y, want, bound, "nb=%d q=%d" % (nb, q))
+
+
+def test_rank_plans_emulate_multi_gpu_on_one_device(qh768):
+    """One-process-per-GPU mode: `world` rank plans (all on cuda:0 here, executed one after
+    the other), every rank's edge block copied into the rank-major table (an NCCL all-gather
+    in bench.py), then each owner's merge kernel."""
+    rng = np.random.default_rng(23)
+    cases = [(qh768["rowptr"], qh768["col"], qh768["val"], qh768["n"])]
+    lens = np.array([3, 1, 50000, 2, 2, 9000, 1, 4, 4], np.int64)
+    rp2, col2, val2 = make_csr(rng, len(lens), 3000, lens)
+    cases.append((rp2, col2, val2, 3000))
+    for rp, col, val, n in cases:
+        m, nnz = len(rp) - 1, int(rp[-1])
+        x, y0 = rng.uniform(0.5, 1.5, n), rng.standard_normal(m)
+        want = oracle.csr_spmv(rp, col, val, x, A, B, y0)
+        bound = oracle.csr_spmv_bound(rp, col, val, x, A, B, y0)
+        for version, world, nb, q in ((sb.V1, 2, 0, 1), (sb.V1, 4, 0, 1), (sb.V1, 8, 0, 1), (sb.V2, 4, nnz // 13, 2),
+                                      (sb.BASELINE, 4, 0, 1)):
+            plans = [sb.Plan.create_rank(version, m, n, nnz, val, rp, col, world, r, 0, kernel=2, nb=nb, q=q)
+                     for r in range(world)]
+            slots = plans[0].edge_slots
+            table = np.zeros(world * max(slots, 1))
+            y = y0.copy()
+            for r, p in enumerate(plans):
+                p.execute(A, x, B, y)        # writes the rows rank r owns; split rows wait for the merge
+                if slots:
+                    sb.memcpy(table[r * slots:], p.edge_ptr(), 8 * slots, 2)
+            d_table = plans[0].x_ptr()       # any device scratch of >= world*slots doubles: reuse rank 0's x
+            assert world * slots <= n
+            sb.memcpy(d_table, table, 8 * world * slots, 1)
+            for r, p in enumerate(plans):
+                p.merge_gathered(d_table, A, B)
+                sb.device_synchronize()
+                ptr, first, rows = p.y_ptr()
+                if rows == 0:
+                    continue
+                ybuf = np.zeros(rows)
+                sb.memcpy(ybuf, ptr, 8 * rows, 2)
+                mine = [s for s in (p.segment(i) for i in range(p.num_segments))
+                        if s["device"] == r and s["end_idx"] >= s["start_idx"]]
+                skip = 1 if (version != sb.BASELINE and mine and mine[0]["start_flag"]) else 0
+                y[first + skip:first + rows] = ybuf[skip:]
+            check_tol(y, want, bound, "rank plans version=%d world=%d" % (version, world))
+            for p in plans:
+                p.destroy()
