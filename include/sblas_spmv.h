@@ -109,6 +109,13 @@ int sblas_spmv_plan_create_rank(sblas_spmv_plan **plan, int version, int m, int 
 int sblas_spmv_plan_execute(sblas_spmv_plan *plan, const double *alpha, const double *x,
                             const double *beta, double *y);
 
+/* The two halves of sblas_spmv_plan_execute, for callers that put their own exchange
+ * between them (rank plans): upload enqueues the H2D copies of x (n doubles) and, when y is
+ * not NULL, of this plan's rows of y; download copies the rows this plan owns back to the
+ * host y and waits for the plan's GPUs. */
+int sblas_spmv_plan_upload(sblas_spmv_plan *plan, const double *x, const double *y);
+int sblas_spmv_plan_download(sblas_spmv_plan *plan, double *y);
+
 /* Device-resident execute: x and y already sit in the plan's device buffers
  * (see sblas_spmv_plan_x / _y); nothing crosses PCIe.  Enqueues on the plan's
  * streams and returns without synchronising unless sync != 0. */

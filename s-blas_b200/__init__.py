@@ -79,6 +79,8 @@ def lib():
     L.sblas_spmv_plan_create_rank.argtypes = [P(_vp), C.c_int, C.c_int, C.c_int, _LL, _vp, _vp, _vp, C.c_int,
                                               C.c_int, C.c_int, C.c_int, _LL, C.c_int, C.c_int]
     L.sblas_spmv_plan_execute.argtypes = [_vp, P(C.c_double), _vp, P(C.c_double), _vp]
+    L.sblas_spmv_plan_upload.argtypes = [_vp, _vp, _vp]
+    L.sblas_spmv_plan_download.argtypes = [_vp, _vp]
     L.sblas_spmv_plan_execute_device.argtypes = [_vp, C.c_double, C.c_double, C.c_int]
     L.sblas_spmv_plan_num_devices.argtypes = [_vp]
     L.sblas_spmv_plan_num_segments.argtypes = [_vp]
@@ -261,6 +263,16 @@ class Plan:
         rc = lib().sblas_spmv_plan_execute(self._h, C.byref(a), _ptr(x), C.byref(b), _ptr(y))
         if rc != 0:
             raise RuntimeError("sblas_spmv_plan_execute rc=%d: %s" % (rc, last_error()))
+
+    def upload(self, x, y=None):
+        rc = lib().sblas_spmv_plan_upload(self._h, _ptr(x), None if y is None else _ptr(y))
+        if rc != 0:
+            raise RuntimeError("sblas_spmv_plan_upload rc=%d: %s" % (rc, last_error()))
+
+    def download(self, y):
+        rc = lib().sblas_spmv_plan_download(self._h, None if y is None else _ptr(y))
+        if rc != 0:
+            raise RuntimeError("sblas_spmv_plan_download rc=%d: %s" % (rc, last_error()))
 
     def execute_device(self, alpha, beta, sync=False):
         rc = lib().sblas_spmv_plan_execute_device(self._h, alpha, beta, 1 if sync else 0)

@@ -601,13 +601,14 @@ fail:
     return rc;
 }
 
-int sblas_spmv_plan_execute(sblas_spmv_plan *P, const double *alpha, const double *x, const double *beta, double *y)
+/* x (and y when beta != 0) from HOST memory to every GPU of the plan, asynchronously on
+ * the plan's streams.  In-process multi-GPU: every GPU uploads its 1/nd slice of x over its
+ * own PCIe link and the slices are exchanged over NVLink (replaces nd full-size H2D copies,
+ * dspmv_mgpu_v1.cu:183). */
+int sblas_spmv_plan_upload(sblas_spmv_plan *P, const double *x, const double *y)
 {
     int rc = 0;
-    const double al = *alpha, be = *beta;
     const int nd = P->ndev;
-    /* ---- x: every GPU uploads its 1/nd slice over its own PCIe link, then the slices
-     * are exchanged over NVLink (replaces nd full-size H2D copies, dspmv_mgpu_v1.cu:183) */
     int live = 0;
     for (int d = 0; d < nd; ++d) if (P->devs[d].seg_begin >= 0) ++live;
     int li = 0;
@@ -618,13 +619,14 @@ int sblas_spmv_plan_execute(sblas_spmv_plan *P, const double *alpha, const doubl
         cudaStream_t st = D->streams[0];
         const long long lo = (long long)P->n * li / live, hi = (long long)P->n * (li + 1) / live;
         D->xs_lo = lo; D->xs_hi = hi;
-        if (hi > lo) CU(cudaMemcpyAsync(D->d_x + lo, x + lo, (size_t)(hi - lo) * sizeof(double), cudaMemcpyHostToDevice, st));
-        if (be != 0.0)
+        if (x && hi > lo)
+            CU(cudaMemcpyAsync(D->d_x + lo, x + lo, (size_t)(hi - lo) * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (y)
             CU(cudaMemcpyAsync(D->d_y, y + D->first_row, (size_t)D->rows * sizeof(double), cudaMemcpyHostToDevice, st));
         CU(cudaEventRecord(D->ev_in, st));
         ++li;
     }
-    if (live > 1) {
+    if (x && live > 1) {
         for (int d = 0; d < nd; ++d) {
             sblas_dev *D = &P->devs[d];
             if (D->seg_begin < 0) continue;
@@ -638,9 +640,18 @@ int sblas_spmv_plan_execute(sblas_spmv_plan *P, const double *alpha, const doubl
                                        (size_t)(O->xs_hi - O->xs_lo) * sizeof(double), D->streams[0]));
             }
         }
+        /* nobody may start overwriting d_x (next upload) before every peer has pulled: the
+         * execute that follows records ev_done per GPU and the download synchronises */
     }
-    if ((rc = sblas_spmv_plan_execute_device(P, al, be, 0)) != 0) return rc;
-    /* ---- y: every GPU downloads the rows it owns (disjoint host ranges) */
+fail:
+    return rc;
+}
+
+/* the rows each GPU owns back to HOST y (disjoint ranges), then wait for every GPU */
+int sblas_spmv_plan_download(sblas_spmv_plan *P, double *y)
+{
+    int rc = 0;
+    const int nd = P->ndev;
     for (int d = 0; d < nd; ++d) {
         sblas_dev *D = &P->devs[d];
         if (D->seg_begin < 0) continue;
@@ -652,7 +663,7 @@ int sblas_spmv_plan_execute(sblas_spmv_plan *P, const double *alpha, const doubl
             const int od = P->rank_mode ? (P->g_owner[og] == P->rank ? 0 : -1) : P->g_owner[og];
             if (od != d) skip = 1;
         }
-        if (D->rows - skip > 0)
+        if (y && D->rows - skip > 0)
             CU(cudaMemcpyAsync(y + D->first_row + skip, D->d_y + skip, (size_t)(D->rows - skip) * sizeof(double),
                                cudaMemcpyDeviceToHost, D->streams[0]));
     }
@@ -664,6 +675,14 @@ int sblas_spmv_plan_execute(sblas_spmv_plan *P, const double *alpha, const doubl
     }
 fail:
     return rc;
+}
+
+int sblas_spmv_plan_execute(sblas_spmv_plan *P, const double *alpha, const double *x, const double *beta, double *y)
+{
+    int rc;
+    if ((rc = sblas_spmv_plan_upload(P, x, *beta != 0.0 ? y : NULL)) != 0) return rc;
+    if ((rc = sblas_spmv_plan_execute_device(P, *alpha, *beta, 0)) != 0) return rc;
+    return sblas_spmv_plan_download(P, y);
 }
 
 /* ------------------------------------------------------------------ accessors */
