@@ -10,9 +10,9 @@ SRC    := s-blas_b200/csrc
 OUT    := s-blas_b200/lib
 INC    := -Iinclude -I$(SRC) -I$(CUDA_HOME)/include
 CFLAGS := -O2 -fPIC -Wall -Wno-unused-function -std=gnu11 $(INC)
-NVFLAGS := $(ARCH) -O3 -lineinfo -Xcompiler -fPIC $(INC)
+NVFLAGS := $(ARCH) -O3 -lineinfo -Xptxas -v -Xcompiler -fPIC $(INC)
 
-OBJS := $(OUT)/sblas_kernels.o $(OUT)/sblas_synth.o $(OUT)/sblas_partition.o $(OUT)/sblas_plan.o \
+OBJS := $(OUT)/sblas_kernels.o $(OUT)/sblas_spmv_tma.o $(OUT)/sblas_synth.o $(OUT)/sblas_partition.o $(OUT)/sblas_plan.o \
         $(OUT)/sblas_api.o $(OUT)/sblas_shim.o
 
 all: $(OUT)/libsblas_spmv.so oracle
@@ -20,7 +20,7 @@ all: $(OUT)/libsblas_spmv.so oracle
 $(OUT):
 	mkdir -p $(OUT)
 
-$(OUT)/%.o: $(SRC)/%.cu include/sblas_device.h | $(OUT)
+$(OUT)/%.o: $(SRC)/%.cu include/sblas_device.h $(SRC)/sblas_dev_common.cuh | $(OUT)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 $(OUT)/%.o: $(SRC)/%.c include/sblas_device.h $(SRC)/sblas_internal.h include/sblas_spmv.h | $(OUT)
 	$(HOSTCC) $(CFLAGS) -c $< -o $@

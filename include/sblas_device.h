@@ -27,6 +27,7 @@ typedef struct sblas_seg_args {
     double *carry;        /* [ntile] tile kernel: sum of the row left open by tile j-1     */
     double *tail;         /* [ntile] tile kernel: partial of a row that leaves tile j      */
     const int *tstart;    /* [ntile+1] first row that STARTS inside tile j                 */
+    const int *tmeta;     /* [4*ntile] per tile {rs, re, start of row rs (clamped), ext}   */
     double alpha, beta;
     int row_lo, row_hi;   /* rows of the segment, inclusive, GPU-local numbering           */
     int nz0, nz1;         /* nnz range [nz0, nz1), GPU-local numbering                     */
@@ -34,14 +35,18 @@ typedef struct sblas_seg_args {
     int skip_last;        /* row whose raw sum goes to edge[1] instead of y (or -1)        */
     int tile0;            /* absolute index of the segment's first tile (nz0 / tile)       */
     int ntile;
+    int nz_total;         /* entries resident on this GPU (bound for bulk copies)          */
+    int pad_;
 } sblas_seg_args;
 
 /* kernel families (the `kernel` argument of the reference API maps onto these,
  * see sblas_plan.c) */
-enum { SBLAS_K_VECTOR = 1, SBLAS_K_TILE = 2 };
+enum { SBLAS_K_VECTOR = 1, SBLAS_K_TILE = 2, SBLAS_K_TMA = 3 };
 
-/* nnz per tile of the tile kernel for a given items-per-thread choice */
+/* nnz per tile of the tile kernel for a given items-per-thread choice (kind TILE),
+ * or of the TMA-pipelined kernel (kind TMA, ipt ignored) */
 int sblas_tile_size(int ipt);
+int sblas_tile_size_kind(int kind, int ipt);
 
 /* int64 harness row pointer slice -> int32 GPU-local row pointer:
  * out[i] = clamp(rp64[i] - first_idx, 0, total_nnz), i in [0,count).  Reproduces
@@ -53,6 +58,9 @@ cudaError_t sblas_launch_rebase_rowptr(const long long *rp64, long long first_id
  * start of tile j (binary search per tile; replaces CSR5's tile pointer
  * generation, spmv/include/detail/cuda/format_cuda.h:21-42). */
 cudaError_t sblas_launch_tile_rows(const sblas_seg_args *a, int tile, int *tstart_out, cudaStream_t s);
+/* tmeta[4*j..] = {rs, re, clamp(rowptr[rs]) or tile end, last owned row leaves the tile}
+ * from tstart and rowptr: everything a tile needs in one 16-byte load. */
+cudaError_t sblas_launch_tile_meta(const sblas_seg_args *a, int tile, int *tmeta_out, cudaStream_t s);
 
 /* y[row_lo..row_hi] = alpha*A_seg*x + beta*y for one segment. kind: SBLAS_K_*;
  * ipt: items per thread of the tile kernel (4, 8 or 16); lanes: lanes per row of

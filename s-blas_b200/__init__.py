@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsblas_spmv.so")
 
 BASELINE, V1, V2 = 0, 1, 2
 SRC_HOST, SRC_DEVICE_SHARD = 0, 1
-K_VECTOR, K_TILE = 1, 2
+K_VECTOR, K_TILE, K_TMA = 1, 2, 3
 COLS_PREFIX, COLS_BANDED, COLS_UNIFORM, COLS_CIRCUIT = 0, 1, 2, 3
 
 _LL = C.c_longlong
@@ -40,9 +40,10 @@ class Part(C.Structure):
 class SegArgs(C.Structure):
     """struct sblas_seg_args (include/sblas_device.h)."""
     _fields_ = [("val", _vp), ("col", _vp), ("rowptr", _vp), ("x", _vp), ("y", _vp), ("edge", _vp),
-                ("carry", _vp), ("tail", _vp), ("tstart", _vp), ("alpha", C.c_double), ("beta", C.c_double),
+                ("carry", _vp), ("tail", _vp), ("tstart", _vp), ("tmeta", _vp), ("alpha", C.c_double), ("beta", C.c_double),
                 ("row_lo", C.c_int), ("row_hi", C.c_int), ("nz0", C.c_int), ("nz1", C.c_int),
-                ("skip_first", C.c_int), ("skip_last", C.c_int), ("tile0", C.c_int), ("ntile", C.c_int)]
+                ("skip_first", C.c_int), ("skip_last", C.c_int), ("tile0", C.c_int), ("ntile", C.c_int),
+                ("nz_total", C.c_int), ("pad_", C.c_int)]
 
 
 _lib = None
@@ -109,6 +110,8 @@ def lib():
     L.sblas_tile_size.argtypes = [C.c_int]
     L.sblas_launch_rebase_rowptr.argtypes = [_vp, _LL, C.c_int, _LL, _vp, _vp]
     L.sblas_launch_tile_rows.argtypes = [P(SegArgs), C.c_int, _vp, _vp]
+    L.sblas_launch_tile_meta.argtypes = [P(SegArgs), C.c_int, _vp, _vp]
+    L.sblas_tile_size_kind.argtypes = [C.c_int, C.c_int]
     L.sblas_launch_spmv_segment.argtypes = [P(SegArgs), C.c_int, C.c_int, C.c_int, _vp]
     L.sblas_launch_edge_merge.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_double, C.c_double, _vp]
     L.sblas_launch_fill_f64.argtypes = [_vp, _LL, C.c_double, _vp]

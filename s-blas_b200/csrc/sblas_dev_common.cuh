@@ -1,0 +1,88 @@
+/* sblas_dev_common.cuh -- device helpers shared by the SpMV kernels (sm_100a). */
+#pragma once
+#include <stdint.h>
+#include "sblas_device.h"
+
+namespace sblas {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+/* write one finished row: edge rows (split between segments) keep their raw sum
+ * for the ordered merge (reference merge: dspmv_mgpu_v1.cu:235-248,
+ * dspmv_mgpu_v2.cu:385-441); beta == 0 does not read y (csrmv convention). */
+__device__ __forceinline__ void emit_row(const sblas_seg_args &a, int r, double s)
+{
+    if (r == a.skip_first) {
+        a.edge[0] = s;
+    } else if (r == a.skip_last) {
+        a.edge[1] = s;
+    } else {
+        double out = a.alpha * s;
+        if (a.beta != 0.0) out += a.beta * a.y[r];
+        a.y[r] = out;
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
+    return v;
+}
+
+/* ---- mbarrier / bulk-copy (TMA) PTX wrappers */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    /* try_wait suspends the warp in hardware up to the time hint, so the loop rarely spins */
+    const uint32_t addr = smem_u32(bar);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(addr), "r"(parity), "r"(0x989680u) : "memory");
+}
+/* 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP).
+ * L2 evict-first: the streamed matrix must not push x out of L2. */
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+}  // namespace sblas

@@ -24,7 +24,7 @@ typedef struct sblas_dev {
     double *d_val; int *d_col; int own_matrix;
     int *d_rowptr; double *d_x; double *d_y;
     double *d_edge; int edge_is_host, edge_bound; void *h_edge_alloc;
-    double *d_carry, *d_tail; int *d_tstart;
+    double *d_carry, *d_tail; int *d_tstart, *d_tmeta;
     /* merge lists of the split rows this GPU owns */
     int nmerge, nmsrc;
     int *d_mrow, *d_mbeg; const double **d_msrc;

@@ -22,12 +22,17 @@
  *                     simple cross-check path.
  */
 #include <stdint.h>
+#include "sblas_dev_common.cuh"
 #include "sblas_device.h"
+
+cudaError_t sblas_launch_tma(const sblas_seg_args *a, cudaStream_t s);      /* sblas_spmv_tma.cu */
+int sblas_tma_tile_size(void);
 
 namespace {
 
+using sblas::emit_row;
+using sblas::kFull;
 constexpr int kThreads = 256;
-constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ void ldg_nc_i4(const int *p, int &a, int &b, int &c, int &d)
 {
@@ -39,22 +44,6 @@ __device__ __forceinline__ void ldg_nc_d4(const double *p, double &a, double &b,
 {
     asm("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
         : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
-}
-
-/* write one finished row: edge rows (split between segments) keep their raw sum
- * for the ordered merge (reference merge: dspmv_mgpu_v1.cu:235-248,
- * dspmv_mgpu_v2.cu:385-441); beta == 0 does not read y (csrmv convention). */
-__device__ __forceinline__ void emit_row(const sblas_seg_args &a, int r, double s)
-{
-    if (r == a.skip_first) {
-        a.edge[0] = s;
-    } else if (r == a.skip_last) {
-        a.edge[1] = s;
-    } else {
-        double out = a.alpha * s;
-        if (a.beta != 0.0) out += a.beta * a.y[r];
-        a.y[r] = out;
-    }
 }
 
 /* ------------------------------------------------------------------ vector kernel */
@@ -278,6 +267,22 @@ __global__ void tile_rows_kernel(const sblas_seg_args a, int tile, int *tstart)
     tstart[j] = out;
 }
 
+__global__ void tile_meta_kernel(const sblas_seg_args a, int tile, int4 *tmeta)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.ntile) return;
+    const long long base = (long long)(a.tile0 + j) * tile;
+    const int T0 = (int)max((long long)a.nz0, base);
+    const int T1 = (int)min((long long)a.nz1, base + tile);
+    const int rs = a.tstart[j], re = a.tstart[j + 1];
+    int start0 = T1, ext = 0;
+    if (re > rs) {
+        start0 = min(max(__ldg(a.rowptr + rs), T0), T1);
+        ext = min(__ldg(a.rowptr + re), a.nz1) > T1;
+    }
+    tmeta[j] = make_int4(rs, re, start0, ext);
+}
+
 __global__ void rebase_rowptr_kernel(const long long *__restrict__ rp64, long long first_idx, int total,
                                      long long count, int *__restrict__ out)
 {
@@ -358,6 +363,18 @@ extern "C" cudaError_t sblas_launch_tile_rows(const sblas_seg_args *a, int tile,
     return cudaGetLastError();
 }
 
+extern "C" cudaError_t sblas_launch_tile_meta(const sblas_seg_args *a, int tile, int *tmeta_out, cudaStream_t s)
+{
+    if (a->ntile <= 0) return cudaSuccess;
+    tile_meta_kernel<<<(a->ntile + 255) / 256, 256, 0, s>>>(*a, tile, reinterpret_cast<int4 *>(tmeta_out));
+    return cudaGetLastError();
+}
+
+extern "C" int sblas_tile_size_kind(int kind, int ipt)
+{
+    return kind == SBLAS_K_TMA ? sblas_tma_tile_size() : kThreads * ipt;
+}
+
 extern "C" cudaError_t sblas_launch_edge_merge(const int *mrow, const int *mbeg, const double *const *msrc,
                                                int nmerge, double *y, double alpha, double beta, cudaStream_t s)
 {
@@ -381,6 +398,13 @@ extern "C" cudaError_t sblas_launch_spmv_segment(const sblas_seg_args *a, int ki
     const long long nrows = (long long)a->row_hi - a->row_lo + 1;
     if (nrows <= 0) return cudaSuccess;
     const long long nnz = (long long)a->nz1 - a->nz0;
+    if (kind == SBLAS_K_TMA && nnz > 0 && a->ntile > 0) {
+        cudaError_t e = sblas_launch_tma(a, s);
+        if (e != cudaSuccess) return e;
+        const int blocks = (int)(((long long)a->ntile * 32 + kThreads - 1) / kThreads);
+        spmv_tile_fixup<<<blocks, kThreads, 0, s>>>(*a, sblas_tma_tile_size());
+        return cudaGetLastError();
+    }
     if (kind == SBLAS_K_TILE && nnz > 0 && a->ntile > 0) {
         switch (ipt) {
         case 4: return launch_tile<4>(a, s);

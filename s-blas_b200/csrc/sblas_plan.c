@@ -79,19 +79,21 @@ static int env_int(const char *name, int dflt)
 }
 
 /* `kernel` of the reference API -> kernel family + tile shape.
- *   1: adaptive -- tile kernel (its per-tile reduction adapts to the rows inside the
- *      tile) for anything big enough to fill the GPU, lanes-per-row kernel otherwise
- *   2: nnz-balanced tile kernel everywhere (the reference's "merge-path" choice)
- *   3: CSR5-style small tiles (1024 nnz) */
+ *   1: adaptive -- the persistent TMA-fed tile kernel (its per-tile reduction adapts to
+ *      the rows inside the tile) for anything big enough to fill the GPU, the
+ *      lanes-per-row kernel otherwise
+ *   2: nnz-balanced TMA tile kernel everywhere (the reference's "merge-path" choice)
+ *   3: CSR5-style small register tiles (1024 nnz, one tile per CTA) */
 static void pick_kernel(int kernel, long long dev_nnz, int *kind, int *ipt)
 {
     *ipt = 16;
-    *kind = SBLAS_K_TILE;
+    *kind = SBLAS_K_TMA;
     if (kernel == 1 && dev_nnz < (long long)env_int("SBLAS_VEC_BELOW", 1 << 16)) *kind = SBLAS_K_VECTOR;
-    if (kernel == 3) *ipt = 4;
+    if (kernel == 3) { *kind = SBLAS_K_TILE; *ipt = 4; }
     const char *k = getenv("SBLAS_KIND");
     if (k && !strcmp(k, "vec")) *kind = SBLAS_K_VECTOR;
     if (k && !strcmp(k, "tile")) *kind = SBLAS_K_TILE;
+    if (k && !strcmp(k, "tma")) *kind = SBLAS_K_TMA;
     const int e = env_int("SBLAS_IPT", 0);
     if (e == 4 || e == 8 || e == 16) *ipt = e;
 }
@@ -103,7 +105,7 @@ static void free_dev(sblas_dev *D)
     if (D->own_matrix) { cudaFree(D->d_val); cudaFree(D->d_col); }
     cudaFree(D->d_rowptr); cudaFree(D->d_x); cudaFree(D->d_y);
     if (D->edge_is_host) cudaFreeHost(D->h_edge_alloc); else if (!D->edge_bound) cudaFree(D->d_edge);
-    cudaFree(D->d_carry); cudaFree(D->d_tail); cudaFree(D->d_tstart);
+    cudaFree(D->d_carry); cudaFree(D->d_tail); cudaFree(D->d_tstart); cudaFree(D->d_tmeta);
     cudaFree(D->d_mrow); cudaFree(D->d_mbeg); cudaFree(D->d_msrc);
     if (D->streams) {
         for (int c = 0; c < D->nstreams; ++c) {
@@ -296,14 +298,16 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
             D->d_val = (double *)val; D->d_col = (int *)col; D->own_matrix = 0;
         } else {
             D->own_matrix = 1;
-            CU(cudaMalloc((void **)&D->d_val, (size_t)(D->nnz > 0 ? D->nnz : 1) * sizeof(double)));
-            CU(cudaMalloc((void **)&D->d_col, (size_t)(D->nnz > 0 ? D->nnz : 1) * sizeof(int)));
+            /* +16: bulk copies round the last tile up to 16 bytes */
+            CU(cudaMalloc((void **)&D->d_val, ((size_t)D->nnz + 16) * sizeof(double)));
+            CU(cudaMalloc((void **)&D->d_col, ((size_t)D->nnz + 16) * sizeof(int)));
             if (D->nnz > 0) {
                 CU(cudaMemcpyAsync(D->d_val, val + D->first_idx, (size_t)D->nnz * sizeof(double), cudaMemcpyHostToDevice, st));
                 CU(cudaMemcpyAsync(D->d_col, col + D->first_idx, (size_t)D->nnz * sizeof(int), cudaMemcpyHostToDevice, st));
             }
         }
-        CU(cudaMalloc((void **)&D->d_rowptr, (size_t)(D->rows + 1) * sizeof(int)));
+        CU(cudaMalloc((void **)&D->d_rowptr, ((size_t)D->rows + 1 + 8) * sizeof(int)));
+        CU(cudaMemsetAsync(D->d_rowptr, 0, ((size_t)D->rows + 1 + 8) * sizeof(int), st));
         CU(cudaMalloc((void **)&D->d_x, (size_t)(P->n > 0 ? P->n : 1) * sizeof(double)));
         CU(cudaMalloc((void **)&D->d_y, (size_t)(D->rows > 0 ? D->rows : 1) * sizeof(double)));
         /* int64 host row pointer slice -> int32 rebased/clamped, on the GPU */
@@ -320,7 +324,7 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
 
         /* ---- segments: kernel choice, tiles */
         pick_kernel(P->kernel, D->nnz, &D->kind, &D->ipt);
-        const int TILE = sblas_tile_size(D->ipt);
+        const int TILE = sblas_tile_size_kind(D->kind, D->ipt);
         long long tiles_total = 0;
         for (int s = D->seg_begin; s < D->seg_end; ++s) {
             sblas_seg *S = &P->segs[s];
@@ -336,11 +340,13 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
             a->skip_last = P->g_sl[S->gidx] ? a->row_hi : -1;
             a->tile0 = a->nz0 / TILE;
             a->ntile = (a->nz1 > a->nz0) ? (int)(((long long)a->nz1 - 1) / TILE - a->tile0 + 1) : 0;
+            a->nz_total = D->nnz;
             S->tile_off = tiles_total;
             tiles_total += a->ntile + 1;
             S->stream = S->lidx % D->nstreams;
         }
-        if (D->kind == SBLAS_K_TILE) {
+        if (D->kind != SBLAS_K_VECTOR) {
+            CU(cudaMalloc((void **)&D->d_tmeta, (size_t)(tiles_total + 1) * 4 * sizeof(int)));
             CU(cudaMalloc((void **)&D->d_tstart, (size_t)(tiles_total + 1) * sizeof(int)));
             CU(cudaMalloc((void **)&D->d_carry, (size_t)(tiles_total + 1) * sizeof(double)));
             CU(cudaMalloc((void **)&D->d_tail, (size_t)(tiles_total + 1) * sizeof(double)));
@@ -351,11 +357,15 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
             a->val = D->d_val; a->col = D->d_col; a->rowptr = D->d_rowptr;
             a->x = D->d_x; a->y = D->d_y;
             a->edge = D->d_edge + 2 * S->lidx;
-            if (D->kind == SBLAS_K_TILE) {
+            if (D->kind != SBLAS_K_VECTOR) {
                 a->tstart = D->d_tstart + S->tile_off;
+                a->tmeta = D->d_tmeta + 4 * S->tile_off;
                 a->carry = D->d_carry + S->tile_off;
                 a->tail = D->d_tail + S->tile_off;
-                if (a->ntile > 0) CU(sblas_launch_tile_rows(a, TILE, D->d_tstart + S->tile_off, st));
+                if (a->ntile > 0) {
+                    CU(sblas_launch_tile_rows(a, TILE, D->d_tstart + S->tile_off, st));
+                    CU(sblas_launch_tile_meta(a, TILE, D->d_tmeta + 4 * S->tile_off, st));
+                }
             }
         }
         CU(cudaStreamSynchronize(st));
@@ -763,7 +773,7 @@ int sblas_spmv_plan_launches(const sblas_spmv_plan *P)
         const sblas_dev *D = &P->devs[P->segs[s].dev];
         const sblas_seg_args *a = &P->segs[s].args;
         if (a->row_hi < a->row_lo) continue;
-        n += (D->kind == SBLAS_K_TILE && a->ntile > 0) ? 2 : 1;
+        n += (D->kind != SBLAS_K_VECTOR && a->ntile > 0) ? 2 : 1;
     }
     for (int d = 0; d < P->ndev; ++d) if (P->devs[d].nmerge > 0) ++n;
     return n;

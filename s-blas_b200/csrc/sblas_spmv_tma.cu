@@ -1,0 +1,313 @@
+/* sblas_spmv_tma.cu -- the main SpMV kernel: persistent, warp-specialised, TMA-fed.
+ *
+ * Replaces cusparseDcsrmv_mp / cusparseDcsrmv (spmv/src/dspmv_mgpu_v1.cu:200,206,
+ * dspmv_mgpu_v2.cu:351,357, dspmv_mgpu_baseline.cu:163) and the CSR5 tile kernels
+ * (spmv/include/detail/cuda/csr5_spmv_cuda.h:275-311) for everything big enough to
+ * fill the GPU.
+ *
+ * SpMV is HBM-bound (12 B streamed per nnz, 2 flop): the kernel is built around keeping
+ * as many bytes in flight per SM as possible with no register or LSU cost:
+ *
+ *   - grid = 2 CTAs per SM, persistent; tile j of 2048 nnz goes to CTA j mod grid
+ *     (nnz-balanced: every CTA streams the same number of bytes, whatever the rows are)
+ *   - one producer warp: a single lane issues 1-D bulk copies (cp.async.bulk, SASS UBLKCP)
+ *     of the tile's val (16 KB), col (8 KB) and -- when the tile holds several rows -- its
+ *     slice of the row pointer into a 3-stage shared-memory ring, completion counted on
+ *     mbarriers, L2 evict-first so the stream does not push x out of L2; the per-tile
+ *     metadata (one int4) is prefetched one round ahead
+ *   - eight consumer warps: read col/val from shared memory with a stride-1 lane mapping
+ *     (so the x gather of neighbouring columns coalesces into 2 L1 wavefronts per request),
+ *     gather x through L1/L2, multiply, and reduce with a strategy chosen per tile:
+ *       <= 1 row starts in the tile (long rows)  -> block reduction from registers
+ *       several rows                             -> products written in place over val,
+ *                                                   G = 1..32 lanes per row (thread-per-row
+ *                                                   for short rows ... warp-per-row)
+ *   - rows that leave their tile are finished by spmv_tile_fixup in a fixed order
+ *     (deterministic; no floating-point atomics).
+ */
+#include <cuda_runtime.h>
+#include "sblas_dev_common.cuh"
+
+namespace {
+
+using namespace sblas;
+
+constexpr int kTile = 2048;                    /* nnz per tile */
+constexpr int kConsumers = 256;                /* consumer threads */
+constexpr int kCWarps = kConsumers / 32;
+constexpr int kThreadsTma = kConsumers + 32;   /* + one producer warp */
+constexpr int kIPT = kTile / kConsumers;       /* 8 products per consumer thread */
+constexpr int kRpCap = 1032;                   /* row-pointer ints staged per tile (x4) */
+constexpr int kStages = 3;
+
+struct __align__(128) Stage {
+    double val[kTile];
+    int col[kTile];
+    int rp[kRpCap];
+    int4 meta;       /* {rs, re, start of row rs clamped to the tile, last row leaves tile} */
+    int rp_off;      /* rp[rp_off + q] == rowptr[rs + q] */
+    int rp_ok;       /* the row pointer slice was staged */
+};
+
+constexpr int kSmemBytes = kStages * (int)sizeof(Stage) + 2 * kStages * 8 + kStages * 2 * kCWarps * 8;
+
+__device__ __forceinline__ void release_stage(uint64_t *empty_bar, int lane)
+{
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar);
+}
+
+__global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_seg_args a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    Stage *st = reinterpret_cast<Stage *>(smem);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)kStages * sizeof(Stage));
+    uint64_t *empty = full + kStages;
+    double *red = reinterpret_cast<double *>(empty + kStages);        /* [kStages buffers][2 sums][8 warps] */
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ncta = gridDim.x, cta = blockIdx.x;
+    const int ntile = a.ntile;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kCWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == kCWarps) {
+        /* ------------------------------------------------------------ producer */
+        if (lane == 0) {
+            const uint64_t pol = policy_evict_first();
+            const int4 *tm = reinterpret_cast<const int4 *>(a.tmeta);
+            int j = cta;
+            int4 mnext = make_int4(0, 0, 0, 0);
+            if (j < ntile) mnext = __ldg(tm + j);
+            int s = 0;
+            uint32_t ph = 0;
+            for (; j < ntile; j += ncta) {
+                const int4 m = mnext;
+                if (j + ncta < ntile) mnext = __ldg(tm + j + ncta);
+                mbar_wait(&empty[s], ph ^ 1u);
+                const long long base = (long long)(a.tile0 + j) * kTile;
+                const int cnt = (int)min((long long)kTile, (long long)a.nz_total - base);
+                const uint32_t vb = ((uint32_t)cnt * 8u + 15u) & ~15u;
+                const uint32_t cb = ((uint32_t)cnt * 4u + 15u) & ~15u;
+                const int rp0 = m.x & ~3;
+                const int rpn = ((m.y - rp0 + 1) + 3) & ~3;
+                const bool rp_ok = (m.y - m.x >= 2) && (rpn <= kRpCap);
+                const uint32_t rb = rp_ok ? (uint32_t)rpn * 4u : 0u;
+                st[s].meta = m;
+                st[s].rp_off = m.x - rp0;
+                st[s].rp_ok = rp_ok ? 1 : 0;
+                mbar_arrive_expect_tx(&full[s], vb + cb + rb);
+                bulk_g2s(st[s].val, a.val + base, vb, &full[s], pol);
+                bulk_g2s(st[s].col, a.col + base, cb, &full[s], pol);
+                if (rp_ok) bulk_g2s(st[s].rp, a.rowptr + rp0, rb, &full[s], pol);
+                if (++s == kStages) { s = 0; ph ^= 1u; }
+            }
+        }
+        return;
+    }
+
+    /* ---------------------------------------------------------------- consumers
+     * Software-pipelined by one tile: the col reads and x gathers of tile k+1 are issued
+     * before tile k is reduced, so the gather latency hides behind the reduction.
+     * Element i of thread t is tile-local index i*256 + t (stride-1 across lanes). */
+    const int t = tid;
+    int j = cta;
+    if (j >= ntile) return;
+    const double *__restrict__ xp = a.x;
+    const int nz0 = a.nz0, nz1 = a.nz1;
+    long long base = (long long)(a.tile0 + j) * kTile;
+    const long long step = (long long)ncta * kTile;
+
+    int4 m;                 /* metadata of the current tile */
+    int lo, hi;             /* its valid tile-local range   */
+    double xv[kIPT];        /* its gathered x values        */
+    int s = 0;
+    uint32_t ph = 0;
+
+    auto gather = [&](const Stage &S, long long b, int4 &mm, int &l, int &h, double (&out)[kIPT]) {
+        mm = S.meta;
+        l = (int)(max((long long)nz0, b) - b);
+        h = (int)(min((long long)nz1, b + kTile) - b);
+        int c[kIPT];
+#pragma unroll
+        for (int i = 0; i < kIPT; ++i) c[i] = S.col[i * kConsumers + t];
+        if (l == 0 && h == kTile) {
+#pragma unroll
+            for (int i = 0; i < kIPT; ++i) out[i] = __ldg(xp + c[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < kIPT; ++i) {
+                const int e = i * kConsumers + t;
+                out[i] = (e >= l && e < h) ? __ldg(xp + c[i]) : 0.0;       /* 0 masks the product */
+            }
+        }
+    };
+
+    mbar_wait(&full[0], 0u);
+    gather(st[0], base, m, lo, hi, xv);
+
+    for (; j < ntile; j += ncta, base += step) {
+        Stage &S = st[s];
+        int sn = s + 1;
+        uint32_t phn = ph;
+        if (sn == kStages) { sn = 0; phn ^= 1u; }
+        /* ---- prefetch the next tile of this CTA */
+        int4 mN = make_int4(0, 0, 0, 0);
+        int loN = 0, hiN = 0;
+        double xvN[kIPT];
+        if (j + ncta < ntile) {
+            mbar_wait(&full[sn], phn);
+            gather(st[sn], base + step, mN, loN, hiN, xvN);
+        } else {
+#pragma unroll
+            for (int i = 0; i < kIPT; ++i) xvN[i] = 0.0;
+        }
+        const int rs = m.x, nown = m.y - m.x;
+        const bool ext = m.w != 0;
+        const int bar_id = 1 + s;
+
+        if (nown <= 1) {
+            /* ---- at most one row starts here: block reduction straight from registers */
+            double sc = 0.0, so = 0.0;
+            if (lo != 0 || hi != kTile) {
+                /* partial tile (first / last of a segment): mask explicitly, the slot may hold
+                 * other segments' entries or stale data outside [lo,hi) */
+                const int lsplit = (int)(m.z - base);
+#pragma unroll
+                for (int i = 0; i < kIPT; ++i) {
+                    const int e = i * kConsumers + t;
+                    if (e >= lo && e < hi) {
+                        const double pr = S.val[e] * xv[i];
+                        if (e < lsplit) sc += pr; else so += pr;
+                    }
+                }
+                sc = warp_sum(sc);
+                so = warp_sum(so);
+            } else if (nown == 0) {
+                double s1 = 0.0;
+#pragma unroll
+                for (int i = 0; i < kIPT; i += 2) {
+                    sc = fma(S.val[i * kConsumers + t], xv[i], sc);
+                    s1 = fma(S.val[(i + 1) * kConsumers + t], xv[i + 1], s1);
+                }
+                sc = warp_sum(sc + s1);
+            } else {
+                const int lsplit = (int)(m.z - base);
+#pragma unroll
+                for (int i = 0; i < kIPT; ++i) {
+                    const int e = i * kConsumers + t;
+                    const double pr = S.val[e] * xv[i];
+                    if (e < lsplit) sc += pr; else so += pr;
+                }
+                sc = warp_sum(sc);
+                so = warp_sum(so);
+            }
+            double *R = red + s * (2 * kCWarps);
+            if (lane == 0) { R[warp] = sc; R[kCWarps + warp] = so; }
+            if (warp != 0) {
+                release_stage(&empty[s], lane);
+                asm volatile("bar.arrive %0, %1;" ::"r"(bar_id), "r"(kConsumers) : "memory");
+            } else {
+                named_bar_sync(bar_id, kConsumers);
+                if (lane == 0) {
+                    double c = 0.0, o = 0.0;
+#pragma unroll
+                    for (int w = 0; w < kCWarps; ++w) { c += R[w]; o += R[kCWarps + w]; }
+                    a.carry[j] = c;
+                    if (nown == 1) {
+                        if (ext) a.tail[j] = o; else emit_row(a, rs, o);
+                    }
+                }
+                /* warp 0 releases last: bounds how far the other warps can run ahead
+                 * (< kStages tiles), which is what makes the R / barrier-id rings safe */
+                release_stage(&empty[s], lane);
+            }
+        } else {
+            /* ---- several rows: products in place over val, G lanes per row */
+            const int T0 = (int)(base + lo), T1 = (int)(base + hi);
+#pragma unroll
+            for (int i = 0; i < kIPT; ++i) {
+                const int e = i * kConsumers + t;
+                S.val[e] = (e >= lo && e < hi) ? S.val[e] * xv[i] : 0.0;
+            }
+            named_bar_sync(bar_id, kConsumers);
+            const int nseg = nown + 1;             /* segment 0 = the row left open by the previous tile */
+            const int avg = (hi - lo) / nseg;
+            int G = 1;
+            while (G < 32 && G * 8 <= avg) G <<= 1;
+            const int ngroups = kConsumers / G;
+            const int grp = t / G, gl = t & (G - 1);
+            const bool staged = S.rp_ok != 0;
+            const int *rpl = S.rp + S.rp_off;      /* rpl[q] == rowptr[rs + q] when staged */
+            const int *rpg = a.rowptr + rs;
+            for (int s0 = 0; s0 < nseg; s0 += ngroups) {
+                const int sg = s0 + grp;           /* segment index */
+                double acc = 0.0;
+                if (sg < nseg) {
+                    /* segment sg = [bound(sg-1), bound(sg)), bound(-1) = lo, bound(q) = clamp(rowptr[rs+q]) */
+                    int b = lo;
+                    if (sg > 0) {
+                        const int v = staged ? rpl[sg - 1] : __ldg(rpg + sg - 1);
+                        b = (int)(min(max(v, T0), T1) - base);
+                    }
+                    const int v2 = staged ? rpl[sg] : __ldg(rpg + sg);
+                    const int e = (int)(min(max(v2, T0), T1) - base);
+                    double acc1 = 0.0;
+                    int k = b + gl;
+                    for (; k + G < e; k += 2 * G) { acc += S.val[k]; acc1 += S.val[k + G]; }
+                    if (k < e) acc += S.val[k];
+                    acc += acc1;
+                }
+                for (int off = G >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(kFull, acc, off);
+                if (sg < nseg && gl == 0) {
+                    if (sg == 0) {
+                        a.carry[j] = acc;
+                    } else if (sg == nown && ext) {
+                        a.tail[j] = acc;
+                    } else {
+                        emit_row(a, rs + sg - 1, acc);
+                    }
+                }
+            }
+            fence_proxy_async_smem();              /* generic writes to the slot before the next bulk copy */
+            release_stage(&empty[s], lane);
+        }
+        /* ---- rotate the pipeline registers */
+        m = mN; lo = loN; hi = hiN; s = sn; ph = phn;
+#pragma unroll
+        for (int i = 0; i < kIPT; ++i) xv[i] = xvN[i];
+    }
+}
+
+int g_sm_count[64] = {0};
+
+}  // namespace
+
+int sblas_tma_tile_size(void) { return kTile; }
+
+cudaError_t sblas_launch_tma(const sblas_seg_args *a, cudaStream_t s)
+{
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 64) return cudaErrorInvalidDevice;
+    if (!attr_done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(spmv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        attr_done[dev] = true;
+    }
+    int grid = 2 * g_sm_count[dev];
+    if (grid > a->ntile) grid = a->ntile;
+    spmv_tma_kernel<<<grid, kThreadsTma, kSmemBytes, s>>>(*a);
+    return cudaGetLastError();
+}

@@ -71,8 +71,7 @@ def test_generator_g200_and_g10000():
                          kernels=(1, 2) if n > 200 else (1, 2, 3), what="g %d" % n)
 
 
-@pytest.mark.parametrize("kind", ["vec", "tile"])
-@pytest.mark.parametrize("ipt", [4, 8, 16])
+@pytest.mark.parametrize("kind,ipt", [("vec", 16), ("tile", 4), ("tile", 8), ("tile", 16), ("tma", 16)])
 def test_random_shapes_each_kernel_family(kind, ipt, monkeypatch):
     """Short rows, empty rows, long rows, rows much longer than a tile, unsorted/duplicate columns."""
     monkeypatch.setenv("SBLAS_KIND", kind)
@@ -86,6 +85,8 @@ def test_random_shapes_each_kernel_family(kind, ipt, monkeypatch):
         "all_long": rng.integers(2000, 9000, size=40),
         "many_empty_then_one": np.concatenate([np.zeros(10000, np.int64), [5], np.zeros(9000, np.int64)]),
         "leading_trailing_empty": np.concatenate([[0, 0, 0], rng.integers(1, 50, size=500), [0, 0]]),
+        "rows_of_two": np.full(40000, 2, np.int64),
+        "rows_of_one_and_empty": rng.integers(0, 2, size=30000),
     }
     for name, lens in shapes.items():
         m, n = len(lens), 4099
