@@ -93,8 +93,8 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
                 const int4 m = mnext;
                 if (j + ncta < ntile) mnext = __ldg(tm + j + ncta);
                 mbar_wait(&empty[s], ph ^ 1u);
-                const long long base = (long long)(a.tile0 + j) * kTile;
-                const int cnt = (int)min((long long)kTile, (long long)a.nz_total - base);
+                const int base = (a.tile0 + j) * kTile;
+                const int cnt = min(kTile, a.nz_total - base);
                 const uint32_t vb = ((uint32_t)cnt * 8u + 15u) & ~15u;
                 const uint32_t cb = ((uint32_t)cnt * 4u + 15u) & ~15u;
                 const int rp0 = m.x & ~3;
@@ -115,16 +115,17 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
     }
 
     /* ---------------------------------------------------------------- consumers
-     * Software-pipelined by one tile: the col reads and x gathers of tile k+1 are issued
-     * before tile k is reduced, so the gather latency hides behind the reduction.
-     * Element i of thread t is tile-local index i*256 + t (stride-1 across lanes). */
+     * Element i of thread t is tile-local index i*256 + t (stride-1 across lanes).
+     * Per tile: (1) multiply the tile's val (shared memory) with the x values gathered one
+     * iteration earlier, (2) issue the col reads + x gathers of the NEXT tile into the same
+     * registers, (3) reduce / emit the current tile while those gathers are in flight. */
     const int t = tid;
     int j = cta;
     if (j >= ntile) return;
     const double *__restrict__ xp = a.x;
     const int nz0 = a.nz0, nz1 = a.nz1;
-    long long base = (long long)(a.tile0 + j) * kTile;
-    const long long step = (long long)ncta * kTile;
+    int base = (a.tile0 + j) * kTile;            /* GPU-local nnz index of the tile (fits int32) */
+    const int step = ncta * kTile;
 
     int4 m;                 /* metadata of the current tile */
     int lo, hi;             /* its valid tile-local range   */
@@ -132,65 +133,54 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
     int s = 0;
     uint32_t ph = 0;
 
-    auto gather = [&](const Stage &S, long long b, int4 &mm, int &l, int &h, double (&out)[kIPT]) {
-        mm = S.meta;
-        l = (int)(max((long long)nz0, b) - b);
-        h = (int)(min((long long)nz1, b + kTile) - b);
-        int c[kIPT];
+    auto gather = [&](const Stage &S, int b) {
+        m = S.meta;
+        lo = max(nz0, b) - b;
+        hi = min(nz1 - b, kTile);
+        unsigned c[kIPT];
 #pragma unroll
-        for (int i = 0; i < kIPT; ++i) c[i] = S.col[i * kConsumers + t];
-        if (l == 0 && h == kTile) {
+        for (int i = 0; i < kIPT; ++i) c[i] = (unsigned)S.col[i * kConsumers + t];
+        if (lo == 0 && hi == kTile) {
 #pragma unroll
-            for (int i = 0; i < kIPT; ++i) out[i] = __ldg(xp + c[i]);
+            for (int i = 0; i < kIPT; ++i) xv[i] = __ldg(xp + c[i]);
         } else {
 #pragma unroll
             for (int i = 0; i < kIPT; ++i) {
                 const int e = i * kConsumers + t;
-                out[i] = (e >= l && e < h) ? __ldg(xp + c[i]) : 0.0;       /* 0 masks the product */
+                xv[i] = (e >= lo && e < hi) ? __ldg(xp + c[i]) : 0.0;
             }
         }
     };
 
     mbar_wait(&full[0], 0u);
-    gather(st[0], base, m, lo, hi, xv);
+    gather(st[0], base);
 
     for (; j < ntile; j += ncta, base += step) {
         Stage &S = st[s];
         int sn = s + 1;
         uint32_t phn = ph;
         if (sn == kStages) { sn = 0; phn ^= 1u; }
-        /* ---- prefetch the next tile of this CTA */
-        int4 mN = make_int4(0, 0, 0, 0);
-        int loN = 0, hiN = 0;
-        double xvN[kIPT];
-        if (j + ncta < ntile) {
-            mbar_wait(&full[sn], phn);
-            gather(st[sn], base + step, mN, loN, hiN, xvN);
-        } else {
-#pragma unroll
-            for (int i = 0; i < kIPT; ++i) xvN[i] = 0.0;
-        }
         const int rs = m.x, nown = m.y - m.x;
         const bool ext = m.w != 0;
+        const int clo = lo, chi = hi;              /* current tile's range (gather overwrites lo/hi) */
+        const int lsplit = m.z - base;
         const int bar_id = 1 + s;
+        const bool has_next = j + ncta < ntile;
 
         if (nown <= 1) {
             /* ---- at most one row starts here: block reduction straight from registers */
             double sc = 0.0, so = 0.0;
-            if (lo != 0 || hi != kTile) {
+            if (clo != 0 || chi != kTile) {
                 /* partial tile (first / last of a segment): mask explicitly, the slot may hold
                  * other segments' entries or stale data outside [lo,hi) */
-                const int lsplit = (int)(m.z - base);
 #pragma unroll
                 for (int i = 0; i < kIPT; ++i) {
                     const int e = i * kConsumers + t;
-                    if (e >= lo && e < hi) {
+                    if (e >= clo && e < chi) {
                         const double pr = S.val[e] * xv[i];
                         if (e < lsplit) sc += pr; else so += pr;
                     }
                 }
-                sc = warp_sum(sc);
-                so = warp_sum(so);
             } else if (nown == 0) {
                 double s1 = 0.0;
 #pragma unroll
@@ -198,22 +188,25 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
                     sc = fma(S.val[i * kConsumers + t], xv[i], sc);
                     s1 = fma(S.val[(i + 1) * kConsumers + t], xv[i + 1], s1);
                 }
-                sc = warp_sum(sc + s1);
+                sc += s1;
             } else {
-                const int lsplit = (int)(m.z - base);
 #pragma unroll
                 for (int i = 0; i < kIPT; ++i) {
                     const int e = i * kConsumers + t;
                     const double pr = S.val[e] * xv[i];
                     if (e < lsplit) sc += pr; else so += pr;
                 }
-                sc = warp_sum(sc);
-                so = warp_sum(so);
             }
+            if (warp != 0) release_stage(&empty[s], lane);     /* slot fully consumed */
+            if (has_next) {
+                mbar_wait(&full[sn], phn);
+                gather(st[sn], base + step);                   /* in flight during the reduction */
+            }
+            sc = warp_sum(sc);
+            if (nown != 0) so = warp_sum(so);
             double *R = red + s * (2 * kCWarps);
             if (lane == 0) { R[warp] = sc; R[kCWarps + warp] = so; }
             if (warp != 0) {
-                release_stage(&empty[s], lane);
                 asm volatile("bar.arrive %0, %1;" ::"r"(bar_id), "r"(kConsumers) : "memory");
             } else {
                 named_bar_sync(bar_id, kConsumers);
@@ -232,15 +225,19 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
             }
         } else {
             /* ---- several rows: products in place over val, G lanes per row */
-            const int T0 = (int)(base + lo), T1 = (int)(base + hi);
+            const int T0 = base + clo, T1 = base + chi;
 #pragma unroll
             for (int i = 0; i < kIPT; ++i) {
                 const int e = i * kConsumers + t;
-                S.val[e] = (e >= lo && e < hi) ? S.val[e] * xv[i] : 0.0;
+                S.val[e] = (e >= clo && e < chi) ? S.val[e] * xv[i] : 0.0;
+            }
+            if (has_next) {
+                mbar_wait(&full[sn], phn);
+                gather(st[sn], base + step);
             }
             named_bar_sync(bar_id, kConsumers);
             const int nseg = nown + 1;             /* segment 0 = the row left open by the previous tile */
-            const int avg = (hi - lo) / nseg;
+            const int avg = (chi - clo) / nseg;
             int G = 1;
             while (G < 32 && G * 8 <= avg) G <<= 1;
             const int ngroups = kConsumers / G;
@@ -253,13 +250,13 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
                 double acc = 0.0;
                 if (sg < nseg) {
                     /* segment sg = [bound(sg-1), bound(sg)), bound(-1) = lo, bound(q) = clamp(rowptr[rs+q]) */
-                    int b = lo;
+                    int b = clo;
                     if (sg > 0) {
                         const int v = staged ? rpl[sg - 1] : __ldg(rpg + sg - 1);
-                        b = (int)(min(max(v, T0), T1) - base);
+                        b = min(max(v, T0), T1) - base;
                     }
                     const int v2 = staged ? rpl[sg] : __ldg(rpg + sg);
-                    const int e = (int)(min(max(v2, T0), T1) - base);
+                    const int e = min(max(v2, T0), T1) - base;
                     double acc1 = 0.0;
                     int k = b + gl;
                     for (; k + G < e; k += 2 * G) { acc += S.val[k]; acc1 += S.val[k + G]; }
@@ -280,10 +277,7 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
             fence_proxy_async_smem();              /* generic writes to the slot before the next bulk copy */
             release_stage(&empty[s], lane);
         }
-        /* ---- rotate the pipeline registers */
-        m = mN; lo = loN; hi = hiN; s = sn; ph = phn;
-#pragma unroll
-        for (int i = 0; i < kIPT; ++i) xv[i] = xvN[i];
+        s = sn; ph = phn;
     }
 }
 
