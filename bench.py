@@ -61,8 +61,14 @@ def workload(name):
                     desc="test_spmv g 100000 (12,500 rows x 90,000 nnz + 87,500 rows x 1,000 nnz = 1,212,500,000 nnz)")
     if name == "big50m":       # BASELINE config 5
         m = 50_000_000
+        return dict(m=m, n=m, row_len=two_block(m, m // 8, 180, 2), cols_mode=sb.COLS_BANDRUN, band=1 << 20,
+                    desc="50M-row ~1.2B-nnz non-uniform (6.25M rows x 180 nnz + 43.75M rows x 2 nnz), banded columns "
+                         "+-2^20 in runs of 16 consecutive columns")
+    if name == "big50m_scatter":
+        m = 50_000_000
         return dict(m=m, n=m, row_len=two_block(m, m // 8, 180, 2), cols_mode=sb.COLS_BANDED, band=1 << 20,
-                    desc="50M-row ~1.2B-nnz non-uniform (6.25M rows x 180 nnz + 43.75M rows x 2 nnz), banded columns +-2^20")
+                    desc="50M-row ~1.2B-nnz non-uniform, banded columns +-2^20, every entry in its own cache line "
+                         "(adversarial for the L1 gather path)")
     if name == "big50m_uniform":
         m = 50_000_000
         return dict(m=m, n=m, row_len=two_block(m, m // 8, 180, 2), cols_mode=sb.COLS_UNIFORM, band=0,

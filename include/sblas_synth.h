@@ -17,7 +17,9 @@ enum {
     SBLAS_COLS_PREFIX = 0,   /* col = j                      (the `g` generator)                 */
     SBLAS_COLS_BANDED = 1,   /* sorted-unique inside a window of +-band around the diagonal      */
     SBLAS_COLS_UNIFORM = 2,  /* sorted-unique, stratified over [0,n)                             */
-    SBLAS_COLS_CIRCUIT = 3   /* 80 % of the rows banded, 20 % uniform (hub rows); long rows uniform */
+    SBLAS_COLS_CIRCUIT = 3,  /* 80 % of the rows banded, 20 % uniform (hub rows); long rows uniform */
+    SBLAS_COLS_BANDRUN = 4   /* banded, in runs of 16 consecutive columns (block-structured / multi-DOF
+                                meshes): run starts are sorted-unique inside the +-band window */
 };
 
 /* Fill val/col for the global nnz range [k0,k1) (written at out[k-k0]) of a matrix

@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsblas_spmv.so")
 BASELINE, V1, V2 = 0, 1, 2
 SRC_HOST, SRC_DEVICE_SHARD = 0, 1
 K_VECTOR, K_TILE, K_TMA = 1, 2, 3
-COLS_PREFIX, COLS_BANDED, COLS_UNIFORM, COLS_CIRCUIT = 0, 1, 2, 3
+COLS_PREFIX, COLS_BANDED, COLS_UNIFORM, COLS_CIRCUIT, COLS_BANDRUN = 0, 1, 2, 3, 4
 
 _LL = C.c_longlong
 _vp = C.c_void_p

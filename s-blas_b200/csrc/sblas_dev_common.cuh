@@ -33,26 +33,26 @@ __device__ __forceinline__ double warp_sum(double v)
 /* ---- mbarrier / bulk-copy (TMA) PTX wrappers */
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+/* all wrappers take 32-bit shared-window addresses (smem_u32 once, integer math after) */
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_fence_init()
 {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     /* try_wait suspends the warp in hardware up to the time hint, so the loop rarely spins */
-    const uint32_t addr = smem_u32(bar);
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -61,14 +61,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "@p bra WAIT_DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
-        "}\n" ::"r"(addr), "r"(parity), "r"(0x989680u) : "memory");
+        "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
 /* 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP).
  * L2 evict-first: the streamed matrix must not push x out of L2. */
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
 }
 __device__ __forceinline__ uint64_t policy_evict_first()
 {

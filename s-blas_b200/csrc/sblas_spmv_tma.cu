@@ -6,7 +6,8 @@
  * fill the GPU.
  *
  * SpMV is HBM-bound (12 B streamed per nnz, 2 flop): the kernel is built around keeping
- * as many bytes in flight per SM as possible with no register or LSU cost:
+ * as many bytes in flight per SM as possible with no register or LSU cost, and around a
+ * short instruction stream per nnz (the part runs into its power cap otherwise):
  *
  *   - grid = 2 CTAs per SM, persistent; tile j of 2048 nnz goes to CTA j mod grid
  *     (nnz-balanced: every CTA streams the same number of bytes, whatever the rows are)
@@ -15,13 +16,16 @@
  *     slice of the row pointer into a 3-stage shared-memory ring, completion counted on
  *     mbarriers, L2 evict-first so the stream does not push x out of L2; the per-tile
  *     metadata (one int4) is prefetched one round ahead
- *   - eight consumer warps: read col/val from shared memory with a stride-1 lane mapping
- *     (so the x gather of neighbouring columns coalesces into 2 L1 wavefronts per request),
- *     gather x through L1/L2, multiply, and reduce with a strategy chosen per tile:
- *       <= 1 row starts in the tile (long rows)  -> block reduction from registers
- *       several rows                             -> products written in place over val,
- *                                                   G = 1..32 lanes per row (thread-per-row
- *                                                   for short rows ... warp-per-row)
+ *   - eight consumer warps, element i of thread t = tile-local index i*256 + t (stride-1
+ *     across lanes, so the x gather of neighbouring columns coalesces).  Per tile:
+ *       (1) multiply val (shared memory) by the x values gathered one iteration earlier,
+ *       (2) issue the col reads + x gathers of the NEXT tile into the same registers,
+ *       (3) reduce the current tile while those gathers are in flight:
+ *             <= 1 row starts in the tile (long rows) -> block reduction from registers;
+ *                only warp 0 waits on the named barrier, the others bar.arrive and go on
+ *             several rows -> products in place over val, then G lanes per row:
+ *                G = 32 warp-per-row, 2..16 sub-warp, 1 thread-per-row; beta*y of the rows a
+ *                lane will write is loaded before the barrier
  *   - rows that leave their tile are finished by spmv_tile_fixup in a fixed order
  *     (deterministic; no floating-point atomics).
  */
@@ -51,19 +55,85 @@ struct __align__(128) Stage {
 
 constexpr int kSmemBytes = kStages * (int)sizeof(Stage) + 2 * kStages * 8 + kStages * 2 * kCWarps * 8;
 
-__device__ __forceinline__ void release_stage(uint64_t *empty_bar, int lane)
+__device__ __forceinline__ void release_stage(uint32_t empty_bar, int lane)
 {
     __syncwarp();
     if (lane == 0) mbar_arrive(empty_bar);
+}
+
+/* finish one row in the several-rows path */
+__device__ __forceinline__ void emit_seg(const sblas_seg_args &a, int j, int sg, int nown, bool ext, int rs,
+                                         double acc, double yv)
+{
+    const int row = rs + sg - 1;
+    if (sg == 0) {
+        a.carry[j] = acc;
+    } else if (sg == nown && ext) {
+        a.tail[j] = acc;
+    } else if (row == a.skip_first) {
+        a.edge[0] = acc;
+    } else if (row == a.skip_last) {
+        a.edge[1] = acc;
+    } else {
+        a.y[row] = a.alpha * acc + a.beta * yv;      /* yv == 0 when beta == 0 */
+    }
+}
+
+/* Several rows in a tile: products already sit in S.val; G lanes reduce each segment.
+ * Segment 0 is the row left open by the previous tile, segment q >= 1 is row rs+q-1;
+ * segment sg = [bound(sg-1), bound(sg)), bound(-1) = clo, bound(q) = clamp(rowptr[rs+q]). */
+template <int G>
+__device__ __forceinline__ void reduce_rows(const sblas_seg_args &a, const Stage &S, int j, int t, int base,
+                                            int clo, int chi, int rs, int nown, bool ext, const double *yin,
+                                            int ypre)
+{
+    constexpr int ngroups = kConsumers / G;
+    const int grp = t / G, gl = t & (G - 1);
+    const int nseg = nown + 1;
+    const int T0 = base + clo, T1 = base + chi;
+    const bool staged = S.rp_ok != 0;
+    const int *rpl = S.rp + S.rp_off;
+    const int *rpg = a.rowptr + rs;
+    int rr = 0;
+    for (int s0 = 0; s0 < nseg; s0 += ngroups, ++rr) {
+        const int sg = s0 + grp;
+        double acc = 0.0;
+        if (sg < nseg) {
+            int b = clo;
+            if (sg > 0) b = min(max(staged ? rpl[sg - 1] : __ldg(rpg + sg - 1), T0), T1) - base;
+            const int e = min(max(staged ? rpl[sg] : __ldg(rpg + sg), T0), T1) - base;
+            double acc1 = 0.0;
+            int k = b + gl;
+            for (; k + G < e; k += 2 * G) { acc += S.val[k]; acc1 += S.val[k + G]; }
+            if (k < e) acc += S.val[k];
+            acc += acc1;
+        }
+#pragma unroll
+        for (int off = G >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(kFull, acc, off);
+        if (sg < nseg && gl == 0) {
+            double yv = 0.0;
+            if (a.beta != 0.0) {
+                if (rr < ypre) {
+                    yv = yin[0];
+#pragma unroll
+                    for (int q = 1; q < 4; ++q) if (rr == q) yv = yin[q];
+                } else if (sg >= 1) {
+                    yv = a.y[rs + sg - 1];
+                }
+            }
+            emit_seg(a, j, sg, nown, ext, rs, acc, yv);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_seg_args a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     Stage *st = reinterpret_cast<Stage *>(smem);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)kStages * sizeof(Stage));
-    uint64_t *empty = full + kStages;
-    double *red = reinterpret_cast<double *>(empty + kStages);        /* [kStages buffers][2 sums][8 warps] */
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t full0 = smem0 + (uint32_t)(kStages * sizeof(Stage));    /* full[s]  = full0 + 8 s  */
+    const uint32_t empty0 = full0 + 8u * kStages;                           /* empty[s] = empty0 + 8 s */
+    double *red = reinterpret_cast<double *>(smem + kStages * sizeof(Stage) + 16 * kStages);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ncta = gridDim.x, cta = blockIdx.x;
@@ -72,8 +142,8 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kCWarps);
+            mbar_init(full0 + 8u * s, 1);
+            mbar_init(empty0 + 8u * s, kCWarps);
         }
         mbar_fence_init();
     }
@@ -92,7 +162,7 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
             for (; j < ntile; j += ncta) {
                 const int4 m = mnext;
                 if (j + ncta < ntile) mnext = __ldg(tm + j + ncta);
-                mbar_wait(&empty[s], ph ^ 1u);
+                mbar_wait(empty0 + 8u * s, ph ^ 1u);
                 const int base = (a.tile0 + j) * kTile;
                 const int cnt = min(kTile, a.nz_total - base);
                 const uint32_t vb = ((uint32_t)cnt * 8u + 15u) & ~15u;
@@ -104,21 +174,19 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
                 st[s].meta = m;
                 st[s].rp_off = m.x - rp0;
                 st[s].rp_ok = rp_ok ? 1 : 0;
-                mbar_arrive_expect_tx(&full[s], vb + cb + rb);
-                bulk_g2s(st[s].val, a.val + base, vb, &full[s], pol);
-                bulk_g2s(st[s].col, a.col + base, cb, &full[s], pol);
-                if (rp_ok) bulk_g2s(st[s].rp, a.rowptr + rp0, rb, &full[s], pol);
+                const uint32_t sbase = smem0 + (uint32_t)(s * sizeof(Stage));
+                const uint32_t fb = full0 + 8u * s;
+                mbar_arrive_expect_tx(fb, vb + cb + rb);
+                bulk_g2s(sbase, a.val + base, vb, fb, pol);
+                bulk_g2s(sbase + kTile * 8, a.col + base, cb, fb, pol);
+                if (rp_ok) bulk_g2s(sbase + kTile * 12, a.rowptr + rp0, rb, fb, pol);
                 if (++s == kStages) { s = 0; ph ^= 1u; }
             }
         }
         return;
     }
 
-    /* ---------------------------------------------------------------- consumers
-     * Element i of thread t is tile-local index i*256 + t (stride-1 across lanes).
-     * Per tile: (1) multiply the tile's val (shared memory) with the x values gathered one
-     * iteration earlier, (2) issue the col reads + x gathers of the NEXT tile into the same
-     * registers, (3) reduce / emit the current tile while those gathers are in flight. */
+    /* ---------------------------------------------------------------- consumers */
     const int t = tid;
     int j = cta;
     if (j >= ntile) return;
@@ -152,7 +220,7 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
         }
     };
 
-    mbar_wait(&full[0], 0u);
+    mbar_wait(full0, 0u);
     gather(st[0], base);
 
     for (; j < ntile; j += ncta, base += step) {
@@ -166,11 +234,13 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
         const int lsplit = m.z - base;
         const int bar_id = 1 + s;
         const bool has_next = j + ncta < ntile;
+        const bool whole = (clo == 0 && chi == kTile);
+        const uint32_t eb = empty0 + 8u * s;
 
         if (nown <= 1) {
             /* ---- at most one row starts here: block reduction straight from registers */
             double sc = 0.0, so = 0.0;
-            if (clo != 0 || chi != kTile) {
+            if (!whole) {
                 /* partial tile (first / last of a segment): mask explicitly, the slot may hold
                  * other segments' entries or stale data outside [lo,hi) */
 #pragma unroll
@@ -197,9 +267,9 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
                     if (e < lsplit) sc += pr; else so += pr;
                 }
             }
-            if (warp != 0) release_stage(&empty[s], lane);     /* slot fully consumed */
+            if (warp != 0) release_stage(eb, lane);            /* slot fully consumed */
             if (has_next) {
-                mbar_wait(&full[sn], phn);
+                mbar_wait(full0 + 8u * sn, phn);
                 gather(st[sn], base + step);                   /* in flight during the reduction */
             }
             sc = warp_sum(sc);
@@ -221,61 +291,56 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
                 }
                 /* warp 0 releases last: bounds how far the other warps can run ahead
                  * (< kStages tiles), which is what makes the R / barrier-id rings safe */
-                release_stage(&empty[s], lane);
+                release_stage(eb, lane);
             }
         } else {
             /* ---- several rows: products in place over val, G lanes per row */
-            const int T0 = base + clo, T1 = base + chi;
+            if (whole) {
 #pragma unroll
-            for (int i = 0; i < kIPT; ++i) {
-                const int e = i * kConsumers + t;
-                S.val[e] = (e >= clo && e < chi) ? S.val[e] * xv[i] : 0.0;
+                for (int i = 0; i < kIPT; ++i) S.val[i * kConsumers + t] *= xv[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < kIPT; ++i) {
+                    const int e = i * kConsumers + t;
+                    S.val[e] = (e >= clo && e < chi) ? S.val[e] * xv[i] : 0.0;
+                }
+            }
+            const int nseg = nown + 1;
+            const int len = chi - clo;             /* mean segment length picks the lanes per row */
+            const int lg = len >= 128 * nseg ? 5 : len >= 64 * nseg ? 4 : len >= 32 * nseg ? 3
+                         : len >= 16 * nseg ? 2 : len >= 8 * nseg ? 1 : 0;
+            /* beta*y of the rows this lane will write: loaded now, used after the reduction,
+             * so the global-load latency hides behind the barrier and the row sums */
+            double yin[4] = {0.0, 0.0, 0.0, 0.0};
+            int ypre = 0;
+            if (a.beta != 0.0) {
+                const int G = 1 << lg, ngroups = kConsumers >> lg;
+                const int grp = t >> lg;
+                const bool lead = (t & (G - 1)) == 0;
+                ypre = min(4, (nseg + ngroups - 1) >> (8 - lg));
+                for (int rr = 0; rr < ypre; ++rr) {
+                    const int sg = rr * ngroups + grp;
+                    const int row = rs + sg - 1;
+                    double v = 0.0;
+                    if (lead && sg >= 1 && sg < nseg && row != a.skip_first && row != a.skip_last) v = a.y[row];
+                    if (rr == 0) yin[0] = v; else if (rr == 1) yin[1] = v; else if (rr == 2) yin[2] = v; else yin[3] = v;
+                }
             }
             if (has_next) {
-                mbar_wait(&full[sn], phn);
+                mbar_wait(full0 + 8u * sn, phn);
                 gather(st[sn], base + step);
             }
             named_bar_sync(bar_id, kConsumers);
-            const int nseg = nown + 1;             /* segment 0 = the row left open by the previous tile */
-            const int avg = (chi - clo) / nseg;
-            int G = 1;
-            while (G < 32 && G * 8 <= avg) G <<= 1;
-            const int ngroups = kConsumers / G;
-            const int grp = t / G, gl = t & (G - 1);
-            const bool staged = S.rp_ok != 0;
-            const int *rpl = S.rp + S.rp_off;      /* rpl[q] == rowptr[rs + q] when staged */
-            const int *rpg = a.rowptr + rs;
-            for (int s0 = 0; s0 < nseg; s0 += ngroups) {
-                const int sg = s0 + grp;           /* segment index */
-                double acc = 0.0;
-                if (sg < nseg) {
-                    /* segment sg = [bound(sg-1), bound(sg)), bound(-1) = lo, bound(q) = clamp(rowptr[rs+q]) */
-                    int b = clo;
-                    if (sg > 0) {
-                        const int v = staged ? rpl[sg - 1] : __ldg(rpg + sg - 1);
-                        b = min(max(v, T0), T1) - base;
-                    }
-                    const int v2 = staged ? rpl[sg] : __ldg(rpg + sg);
-                    const int e = min(max(v2, T0), T1) - base;
-                    double acc1 = 0.0;
-                    int k = b + gl;
-                    for (; k + G < e; k += 2 * G) { acc += S.val[k]; acc1 += S.val[k + G]; }
-                    if (k < e) acc += S.val[k];
-                    acc += acc1;
-                }
-                for (int off = G >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(kFull, acc, off);
-                if (sg < nseg && gl == 0) {
-                    if (sg == 0) {
-                        a.carry[j] = acc;
-                    } else if (sg == nown && ext) {
-                        a.tail[j] = acc;
-                    } else {
-                        emit_row(a, rs + sg - 1, acc);
-                    }
-                }
+            switch (lg) {
+            case 5: reduce_rows<32>(a, S, j, t, base, clo, chi, rs, nown, ext, yin, ypre); break;
+            case 4: reduce_rows<16>(a, S, j, t, base, clo, chi, rs, nown, ext, yin, ypre); break;
+            case 3: reduce_rows<8>(a, S, j, t, base, clo, chi, rs, nown, ext, yin, ypre); break;
+            case 2: reduce_rows<4>(a, S, j, t, base, clo, chi, rs, nown, ext, yin, ypre); break;
+            case 1: reduce_rows<2>(a, S, j, t, base, clo, chi, rs, nown, ext, yin, ypre); break;
+            default: reduce_rows<1>(a, S, j, t, base, clo, chi, rs, nown, ext, yin, ypre); break;
             }
             fence_proxy_async_smem();              /* generic writes to the slot before the next bulk copy */
-            release_stage(&empty[s], lane);
+            release_stage(eb, lane);
         }
         s = sn; ph = phn;
     }

@@ -41,6 +41,8 @@ __global__ void fill_csr_kernel(const long long *__restrict__ rp, int row_first,
             m = (hub || len > 2 * band) ? SBLAS_COLS_UNIFORM : SBLAS_COLS_BANDED;
         }
         long long W = n, start = 0;
+        const bool runs = (m == SBLAS_COLS_BANDRUN);
+        if (runs) m = SBLAS_COLS_BANDED;
         if (m == SBLAS_COLS_BANDED) {
             W = 2 * band < n ? 2 * band : n;
             if (W < len) W = len < n ? len : n;
@@ -54,6 +56,15 @@ __global__ void fill_csr_kernel(const long long *__restrict__ rp, int row_first,
             const uint64_t h = mix64(seed ^ (uint64_t)k);
             int c;
             if (m == SBLAS_COLS_PREFIX) c = (int)(j < n ? j : n - 1);
+            else if (runs && len <= W / 16) {
+                /* run r = j/16 starts at a stratified multiple of 16 inside the window */
+                const long long nrun = (len + 15) / 16, r = j / 16;
+                const uint64_t hr = mix64(seed ^ (uint64_t)(b + r * 16) * 0x9E37ull);
+                const long long cell = (W / 16) / nrun;                 /* >= 1 slots of 16 columns per run */
+                const long long slot = r * cell + (long long)(hr % (uint64_t)cell);
+                long long cc = start + slot * 16 + (j - r * 16);
+                c = (int)(cc < n ? cc : n - 1);
+            }
             else if (len <= W) c = strat_col(start, W, len, j, h);
             else c = (int)(j % n);
             col[k - k0] = c;
