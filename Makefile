@@ -15,7 +15,7 @@ NVFLAGS := $(ARCH) -O3 -lineinfo -Xptxas -v -Xcompiler -fPIC $(INC)
 OBJS := $(OUT)/sblas_kernels.o $(OUT)/sblas_spmv_tma.o $(OUT)/sblas_synth.o $(OUT)/sblas_partition.o $(OUT)/sblas_plan.o \
         $(OUT)/sblas_api.o $(OUT)/sblas_shim.o
 
-all: $(OUT)/libsblas_spmv.so oracle
+all: $(OUT)/libsblas_spmv.so test_spmv oracle
 
 $(OUT):
 	mkdir -p $(OUT)
@@ -31,10 +31,11 @@ $(OUT)/libsblas_spmv.so: $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart shared -Xlinker -rpath,$(CUDA_HOME)/lib64 -lm
 
 test_spmv: $(SRC)/test_spmv.c $(OUT)/libsblas_spmv.so
-	$(HOSTCC) -O2 -Wall -std=gnu11 $(INC) $< -o $@ -L$(OUT) -lsblas_spmv -Wl,-rpath,'$$ORIGIN/$(OUT)' -lm
+	$(HOSTCC) -O2 -Wall -std=gnu11 $(INC) $< -o $@ -L$(OUT) -lsblas_spmv -L$(CUDA_HOME)/lib64 -lcudart -Wl,-rpath,'$$ORIGIN/$(OUT)' -Wl,-rpath,$(CUDA_HOME)/lib64 -lm
 
-oracle:
+oracle: $(OUT)/libsblas_spmv.so
 	$(MAKE) -C oracle -s
+	$(MAKE) -C oracle -s refharness
 
 clean:
 	rm -rf $(OUT) test_spmv; $(MAKE) -C oracle clean

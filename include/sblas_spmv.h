@@ -96,7 +96,7 @@ int sblas_spmv_plan_create(sblas_spmv_plan **plan, int version, int m, int n, lo
  * in which case csrVal/csrColIndex are DEVICE pointers to exactly this rank's
  * nnz range [start_idx, end_idx] (adopted, not copied) and csrRowPtr is still
  * the whole host row pointer. */
-enum { SBLAS_SRC_HOST = 0, SBLAS_SRC_DEVICE_SHARD = 1 };
+enum { SBLAS_SRC_HOST = 0, SBLAS_SRC_DEVICE_SHARD = 1, SBLAS_LAYOUT_ONLY = 2 };
 int sblas_spmv_plan_create_rank(sblas_spmv_plan **plan, int version, int m, int n, long long nnz,
                                 const double *csrVal, const long long *csrRowPtr, const int *csrColIndex,
                                 int world, int rank, int device, int kernel, long long nb, int q, int flags);
@@ -134,6 +134,18 @@ void *sblas_spmv_plan_stream(sblas_spmv_plan *plan, int dev);         /* cudaStr
 int sblas_spmv_plan_edges(sblas_spmv_plan *plan, double *out);
 /* device pointer of the edge table of one GPU (2 doubles per local segment) */
 double *sblas_spmv_plan_edge_ptr(sblas_spmv_plan *plan, int dev);
+/* Host-side layout of a plan, without touching a GPU (flags |= SBLAS_LAYOUT_ONLY in
+ * sblas_spmv_plan_create_rank builds only this): the segments this process runs and the
+ * merge lists of the split rows it owns.  Used by the CPU tests of the multi-rank path.
+ *   local_segment: out = {global segment, first row, last row, first nnz, end nnz (exclusive),
+ *                         first row shared, last row shared, edge slot, GPU index, GPU's first row}
+ *   merge_list:    row i (GPU-local index mrow[i]) = alpha * sum of table[msrc_off[k]],
+ *                  k in [mbeg[i], mbeg[i+1]), + beta*y; table = rank-major gathered edges */
+int sblas_spmv_plan_local_segments(const sblas_spmv_plan *plan);
+int sblas_spmv_plan_local_segment(const sblas_spmv_plan *plan, int i, long long out[10]);
+int sblas_spmv_plan_merge_list(const sblas_spmv_plan *plan, int dev, int *nmerge, const int **mrow,
+                               const int **mbeg, const long long **msrc_off);
+
 /* Rank plans: number of doubles each rank contributes to the exchange of split-row
  * partials (2 per local segment, padded to the largest rank), and the merge that
  * finishes the rows this rank owns from a table holding every rank's block

@@ -1,0 +1,83 @@
+#!/usr/bin/env python3
+"""run_test.py -- Python 3 port of the SpMV half of the reference driver (run_test.py:1-66,
+179-186 of pnnl/s-blas; the original is Python 2 and also drives spmm/sptrsv/sptrans, which
+are outside this repo's path).  Same behaviour for SpMV: for every matrix in matrices.txt
+and every GPU count 1..n_gpus it runs
+
+    ./test_spmv f <mtxpath><matrix> <gpu> 1 1 f
+
+scrapes the `m:` and `Average` lines exactly like parse_spmv (run_test.py:29-43) and writes
+results.csv with the labels V1/V2/V3 = baseline/v1/v2.  Extra columns (gflops) are appended
+after the reference's eight so existing readers keep working.
+"""
+import os
+import subprocess
+import sys
+
+n_gpus = int(os.environ.get("SBLAS_NGPUS", "2"))
+mtxpath = os.environ.get("SBLAS_MTXPATH", "./sample_matrix/")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def ensure_sample_matrix():
+    """The reference bundles sample_matrix/qh768.mtx; here it is regenerated from the golden
+    fixture (same entries, same order) when missing."""
+    p = os.path.join(mtxpath, "qh768.mtx")
+    if os.path.exists(p):
+        return
+    import numpy as np
+    g = np.load(os.path.join(HERE, "tests", "golden", "qh768_coo.npz"))
+    os.makedirs(mtxpath, exist_ok=True)
+    with open(p, "w") as fh:
+        fh.write("%%MatrixMarket matrix coordinate real general\n")
+        fh.write("% Bai/qh768 regenerated from tests/golden/qh768_coo.npz (file order preserved)\n")
+        fh.write("%d %d %d\n" % (int(g["m"]), int(g["n"]), len(g["val"])))
+        for r, c, v in zip(g["row"], g["col"], g["val"]):
+            fh.write("%d %d %s\n" % (r + 1, c + 1, repr(float(v))))
+
+
+def parse_spmv(result):
+    m = n = nnz = 0
+    v1_time = v2_time = v3_time = float("nan")
+    for line in result.strip().split("\n"):
+        l = line.strip()
+        if l.startswith("m:"):
+            words = l.strip("\n").split(" ")
+            m = int(words[1])
+            n = int(words[3])
+            nnz = int(words[5])
+        if l.startswith("Average"):
+            words = [i for i in l.strip("\n").split(" ") if i]
+            v1_time = float(words[1])
+            v2_time = float(words[2])
+            v3_time = float(words[3])
+    return m, n, nnz, v1_time, v2_time, v3_time
+
+
+def test_spmv(mtxlist, result_file):
+    result_file.write("kernel, matrix, n_gpu, m, n, nnz, version, time, gflops\n")
+    for mtx in mtxlist:
+        for gpu in range(1, n_gpus + 1):
+            cmd = "./test_spmv f " + mtxpath + mtx + " " + str(gpu) + " 1 " + "1 f"
+            print(cmd)
+            result = subprocess.run(cmd, shell=True, capture_output=True, text=True, cwd=HERE).stdout
+            m, n, nnz, v1_time, v2_time, v3_time = parse_spmv(result)
+            for label, t in (("V1", v1_time), ("V2", v2_time), ("V3", v3_time)):
+                result_file.write("spmv, %s, %d, %d, %d, %d, %s, %s, %s\n" % (
+                    mtx, gpu, m, n, nnz, label, t, (2.0 * nnz / t / 1e9) if t == t and t > 0 else "nan"))
+    result_file.write("\n")
+
+
+def main():
+    listing = os.path.join(HERE, "matrices.txt")
+    mtxlist = [l.strip() for l in open(listing)] if os.path.exists(listing) else ["qh768.mtx"]
+    mtxlist = [l for l in mtxlist if l]
+    print("The following matrices will be tested:")
+    print(mtxlist)
+    ensure_sample_matrix()
+    with open(os.path.join(HERE, "results.csv"), "w") as fh:
+        test_spmv(mtxlist, fh)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

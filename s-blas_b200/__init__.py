@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsblas_spmv.so")
 
 BASELINE, V1, V2 = 0, 1, 2
-SRC_HOST, SRC_DEVICE_SHARD = 0, 1
+SRC_HOST, SRC_DEVICE_SHARD, LAYOUT_ONLY = 0, 1, 2
 K_VECTOR, K_TILE, K_TMA = 1, 2, 3
 COLS_PREFIX, COLS_BANDED, COLS_UNIFORM, COLS_CIRCUIT, COLS_BANDRUN = 0, 1, 2, 3, 4
 
@@ -100,6 +100,9 @@ def lib():
     L.sblas_spmv_plan_edge_slots.argtypes = [_vp]
     L.sblas_spmv_plan_merge_gathered.argtypes = [_vp, _vp, C.c_double, C.c_double]
     L.sblas_spmv_plan_bind_edge_table.argtypes = [_vp, _vp]
+    L.sblas_spmv_plan_local_segments.argtypes = [_vp]
+    L.sblas_spmv_plan_local_segment.argtypes = [_vp, C.c_int, P(_LL)]
+    L.sblas_spmv_plan_merge_list.argtypes = [_vp, C.c_int, P(C.c_int), P(P(C.c_int)), P(P(C.c_int)), P(P(_LL))]
     L.sblas_memcpy.argtypes = [_vp, _vp, C.c_ulonglong, C.c_int]
     L.sblas_spmv_plan_alg_bytes.argtypes = [_vp, C.c_int, _LL]
     L.sblas_spmv_plan_alg_bytes.restype = C.c_double
@@ -320,6 +323,23 @@ class Plan:
 
     def edge_ptr(self, dev=0):
         return lib().sblas_spmv_plan_edge_ptr(self._h, dev)
+
+    def local_segments(self):
+        """Host layout: the segments this process runs (see sblas_spmv_plan_local_segment)."""
+        keys = ("gidx", "row_lo", "row_hi", "nz0", "nz1", "shared_first", "shared_last", "edge_slot", "dev", "dev_first_row")
+        out = []
+        for i in range(lib().sblas_spmv_plan_local_segments(self._h)):
+            buf = (_LL * 10)()
+            assert lib().sblas_spmv_plan_local_segment(self._h, i, buf) == 0
+            out.append(dict(zip(keys, [int(v) for v in buf])))
+        return out
+
+    def merge_list(self, dev=0):
+        """Host layout: [(GPU-local row, [offsets into the rank-major edge table])] this GPU finishes."""
+        n = C.c_int()
+        mrow, mbeg, moff = C.POINTER(C.c_int)(), C.POINTER(C.c_int)(), C.POINTER(_LL)()
+        assert lib().sblas_spmv_plan_merge_list(self._h, dev, C.byref(n), C.byref(mrow), C.byref(mbeg), C.byref(moff)) == 0
+        return [(mrow[i], [int(moff[k]) for k in range(mbeg[i], mbeg[i + 1])]) for i in range(n.value)]
 
     def bind_edge_table(self, device_ptr):
         assert lib().sblas_spmv_plan_bind_edge_table(self._h, int(device_ptr)) == 0

@@ -36,7 +36,7 @@ typedef struct sblas_dev {
 } sblas_dev;
 
 struct sblas_spmv_plan {
-    int version, m, n, kernel, q, world, rank, rank_mode, ndev, p2p;
+    int version, m, n, kernel, q, world, rank, rank_mode, ndev, p2p, dry;
     long long nnz, nb;
     /* global partition, identical on every rank */
     int nparts; sblas_part *parts;

@@ -99,8 +99,12 @@ static void pick_kernel(int kernel, long long dev_nnz, int *kind, int *ipt)
 }
 
 /* ------------------------------------------------------------------ build */
-static void free_dev(sblas_dev *D)
+static void free_dev(sblas_dev *D, int dry)
 {
+    if (dry) {
+        free(D->h_mrow); free(D->h_mbeg); free(D->h_msrc); free(D->h_msrc_off);
+        return;
+    }
     if (D->device >= 0) cudaSetDevice(D->device);
     if (D->own_matrix) { cudaFree(D->d_val); cudaFree(D->d_col); }
     cudaFree(D->d_rowptr); cudaFree(D->d_x); cudaFree(D->d_y);
@@ -122,7 +126,7 @@ static void free_dev(sblas_dev *D)
 void sblas_spmv_plan_destroy(sblas_spmv_plan *P)
 {
     if (!P) return;
-    for (int d = 0; d < P->ndev; ++d) free_dev(&P->devs[d]);
+    for (int d = 0; d < P->ndev; ++d) free_dev(&P->devs[d], P->dry);
     free(P->devs); free(P->segs); free(P->parts); free(P->g_owner); free(P->g_local);
     free(P->g_lo); free(P->g_hi); free(P->g_sf); free(P->g_sl);
     free(P);
@@ -208,6 +212,8 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
 {
     int rc = 0;
     long long *stage64 = NULL;
+    const int dry = (src_flags & SBLAS_LAYOUT_ONLY) != 0;     /* host layout only: no CUDA call at all */
+    P->dry = dry;
     if (build_global(P, rp) != 0) { sblas_set_error("%s%s (line %d)", "partition failed", "", __LINE__); return -1; }
 
     /* ---- local segments per GPU */
@@ -269,7 +275,9 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
             return -1;
         }
         D->nnz = (int)(dn < 0 ? 0 : dn);
+        D->nstreams = P->q > 1 ? P->q : 1;
 
+        if (!dry) {
         CU(cudaSetDevice(D->device));
         /* memory guard of the reference: shard > 0.8 x free -> -1
          * (dspmv_mgpu_baseline.cu:70-79, dspmv_mgpu_v1.cu:106-116) */
@@ -283,7 +291,6 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
                 rc = -1; goto fail;
             }
         }
-        D->nstreams = P->q > 1 ? P->q : 1;
         D->streams = (cudaStream_t *)calloc((size_t)D->nstreams, sizeof(cudaStream_t));
         D->ev_seg = (cudaEvent_t *)calloc((size_t)D->nstreams, sizeof(cudaEvent_t));
         for (int c = 0; c < D->nstreams; ++c) {
@@ -293,6 +300,7 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
         CU(cudaEventCreateWithFlags(&D->ev_in, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&D->ev_done, cudaEventDisableTiming));
         cudaStream_t st = D->streams[0];
+        (void)st;
 
         if (src_flags & SBLAS_SRC_DEVICE_SHARD) {
             D->d_val = (double *)val; D->d_col = (int *)col; D->own_matrix = 0;
@@ -321,6 +329,7 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
         const int nl = D->seg_end - D->seg_begin;
         CU(cudaMalloc((void **)&D->d_edge, (size_t)(2 * (P->rank_mode ? P->max_local : nl) + 2) * sizeof(double)));
         CU(cudaMemsetAsync(D->d_edge, 0, (size_t)(2 * (P->rank_mode ? P->max_local : nl) + 2) * sizeof(double), st));
+        }   /* !dry */
 
         /* ---- segments: kernel choice, tiles */
         pick_kernel(P->kernel, D->nnz, &D->kind, &D->ipt);
@@ -345,6 +354,8 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
             tiles_total += a->ntile + 1;
             S->stream = S->lidx % D->nstreams;
         }
+        if (dry) continue;
+        cudaStream_t st = D->streams[0];
         if (D->kind != SBLAS_K_VECTOR) {
             CU(cudaMalloc((void **)&D->d_tmeta, (size_t)(tiles_total + 1) * 4 * sizeof(int)));
             CU(cudaMalloc((void **)&D->d_tstart, (size_t)(tiles_total + 1) * sizeof(int)));
@@ -373,7 +384,7 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
 
     /* ---- peer access between the GPUs of an in-process plan */
     P->p2p = 0;
-    if (!P->rank_mode && ndev > 1) {
+    if (!dry && !P->rank_mode && ndev > 1) {
         P->p2p = 1;
         for (int a = 0; a < ndev && P->p2p; ++a)
             for (int b = 0; b < ndev; ++b) {
@@ -443,7 +454,7 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
         }
         D->nmerge = nrow; D->nmsrc = nsrc;
         D->h_mbeg[nrow] = nsrc;
-        if (nrow > 0) {
+        if (nrow > 0 && !dry) {
             CU(cudaSetDevice(D->device));
             CU(cudaMalloc((void **)&D->d_mrow, (size_t)nrow * sizeof(int)));
             CU(cudaMalloc((void **)&D->d_mbeg, (size_t)(nrow + 1) * sizeof(int)));
@@ -518,7 +529,7 @@ int sblas_spmv_plan_create_rank(sblas_spmv_plan **plan, int version, int m, int 
                                 int world, int rank, int device, int kernel, long long nb, int q, int flags)
 {
     if (rank < 0 || rank >= world) return -1;
-    if (cudaSetDevice(device) != cudaSuccess) {
+    if (!(flags & SBLAS_LAYOUT_ONLY) && cudaSetDevice(device) != cudaSuccess) {
         cudaGetLastError();
         sblas_set_error("%s%s (line %d)", "cudaSetDevice failed (no CPU fallback)", "", __LINE__);
         return 1;
@@ -696,6 +707,36 @@ int sblas_spmv_plan_execute(sblas_spmv_plan *P, const double *alpha, const doubl
 }
 
 /* ------------------------------------------------------------------ accessors */
+int sblas_spmv_plan_local_segments(const sblas_spmv_plan *P) { return P->nseg; }
+
+int sblas_spmv_plan_local_segment(const sblas_spmv_plan *P, int i, long long out[10])
+{
+    if (i < 0 || i >= P->nseg) return -1;
+    const sblas_seg *S = &P->segs[i];
+    const sblas_dev *D = &P->devs[S->dev];
+    out[0] = S->gidx;
+    out[1] = P->g_lo[S->gidx];
+    out[2] = P->g_hi[S->gidx];
+    out[3] = D->first_idx + S->args.nz0;
+    out[4] = D->first_idx + S->args.nz1;
+    out[5] = P->g_sf[S->gidx];
+    out[6] = P->g_sl[S->gidx];
+    out[7] = 2LL * S->lidx;
+    out[8] = S->dev;
+    out[9] = D->first_row;
+    return 0;
+}
+
+int sblas_spmv_plan_merge_list(const sblas_spmv_plan *P, int dev, int *nmerge, const int **mrow, const int **mbeg,
+                               const long long **msrc_off)
+{
+    if (dev < 0 || dev >= P->ndev) return -1;
+    const sblas_dev *D = &P->devs[dev];
+    *nmerge = D->nmerge;
+    *mrow = D->h_mrow; *mbeg = D->h_mbeg; *msrc_off = D->h_msrc_off;
+    return 0;
+}
+
 int sblas_spmv_plan_num_devices(const sblas_spmv_plan *P) { return P->ndev; }
 int sblas_spmv_plan_num_segments(const sblas_spmv_plan *P) { return P->nparts; }
 int sblas_spmv_plan_segment(const sblas_spmv_plan *P, int seg, sblas_part *out, int *device)
