@@ -402,6 +402,12 @@ def main():
         # dominant kernel = spmv_tile_kernel on rank 0's shard; its launch (+ the few-us fix-up) is the N=1 step
         k_ms = float(np.median(per)) if world == 1 else None
         ach = alg_rank0 / (float(np.mean(per)) * 1e-3) / 1e9
+        traffic = None            # dram bytes read+written per launch from the committed ncu capture, if any
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tr.get("%s:n%d" % (args.workload, world), {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
         out = {
             "metric": "double CSR SpMV GFLOP/s", "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -412,8 +418,8 @@ def main():
             "hbm_gbs": alg_total / (ms_step * 1e-3) / 1e9,
             "hbm_frac_of_8000": alg_total / (ms_step * 1e-3) / 1e9 / (8000.0 * world),
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "kernel": "spmv_tile_kernel<16> (+ spmv_tile_fixup) on rank 0's shard",
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "spmv_tma_kernel (+ spmv_tile_fixup) on rank 0's shard",
                          "alg_bytes_per_launch": alg_rank0, "ms_per_launch_mean": float(np.mean(per)),
                          "ms_per_launch_median": k_ms},
             "e2e": {"value": 2.0 * nnz / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d,
