@@ -73,6 +73,14 @@ def workload(name):
         m = 50_000_000
         return dict(m=m, n=m, row_len=two_block(m, m // 8, 180, 2), cols_mode=sb.COLS_UNIFORM, band=0,
                     desc="50M-row ~1.2B-nnz non-uniform, uniform columns (adversarial x traffic)")
+    if name == "rows180":      # diagnostic: the long-row block of big50m alone
+        m = 6_250_000
+        return dict(m=m, n=50_000_000, row_len=two_block(m, m, 180, 180), cols_mode=sb.COLS_BANDRUN, band=1 << 20,
+                    desc="diagnostic: 6.25M rows x 180 nnz, banded runs")
+    if name == "rows2":        # diagnostic: the short-row block of big50m alone
+        m = 43_750_000
+        return dict(m=m, n=50_000_000, row_len=two_block(m, m, 2, 2), cols_mode=sb.COLS_BANDRUN, band=1 << 20,
+                    desc="diagnostic: 43.75M rows x 2 nnz, banded runs")
     if name == "circuit5m":    # BASELINE config 3
         m = 5_558_326
 

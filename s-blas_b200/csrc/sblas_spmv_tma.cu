@@ -43,6 +43,7 @@ constexpr int kThreadsTma = kConsumers + 32;   /* + one producer warp */
 constexpr int kIPT = kTile / kConsumers;       /* 8 products per consumer thread */
 constexpr int kRpCap = 1032;                   /* row-pointer ints staged per tile (x4) */
 constexpr int kStages = 3;
+constexpr int kChunk = kTile / kCWarps;             /* entries owned by one consumer warp */
 
 struct __align__(128) Stage {
     double val[kTile];
@@ -53,7 +54,7 @@ struct __align__(128) Stage {
     int rp_ok;       /* the row pointer slice was staged */
 };
 
-constexpr int kSmemBytes = kStages * (int)sizeof(Stage) + 2 * kStages * 8 + kStages * 2 * kCWarps * 8;
+constexpr int kSmemBytes = kStages * (int)sizeof(Stage) + 2 * kStages * 8 + kStages * (2 + 3) * kCWarps * 8;
 
 __device__ __forceinline__ void release_stage(uint32_t empty_bar, int lane)
 {
@@ -186,7 +187,9 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
         return;
     }
 
-    /* ---------------------------------------------------------------- consumers */
+    /* ---------------------------------------------------------------- consumers
+     * Element i of a thread is tile-local index  warp*256 + i*32 + lane : every warp owns a
+     * contiguous 256-entry chunk of the tile, lanes are stride-1 inside it. */
     const int t = tid;
     int j = cta;
     if (j >= ntile) return;
@@ -194,6 +197,8 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
     const int nz0 = a.nz0, nz1 = a.nz1;
     int base = (a.tile0 + j) * kTile;            /* GPU-local nnz index of the tile (fits int32) */
     const int step = ncta * kTile;
+    const int c0 = warp * kChunk;                /* my warp's chunk [c0, c0 + 256) */
+    const int e0 = c0 + lane;                    /* my element i is e0 + 32 i */
 
     int4 m;                 /* metadata of the current tile */
     int lo, hi;             /* its valid tile-local range   */
@@ -207,14 +212,14 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
         hi = min(nz1 - b, kTile);
         unsigned c[kIPT];
 #pragma unroll
-        for (int i = 0; i < kIPT; ++i) c[i] = (unsigned)S.col[i * kConsumers + t];
+        for (int i = 0; i < kIPT; ++i) c[i] = (unsigned)S.col[e0 + 32 * i];
         if (lo == 0 && hi == kTile) {
 #pragma unroll
             for (int i = 0; i < kIPT; ++i) xv[i] = __ldg(xp + c[i]);
         } else {
 #pragma unroll
             for (int i = 0; i < kIPT; ++i) {
-                const int e = i * kConsumers + t;
+                const int e = e0 + 32 * i;
                 xv[i] = (e >= lo && e < hi) ? __ldg(xp + c[i]) : 0.0;
             }
         }
@@ -236,16 +241,17 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
         const bool has_next = j + ncta < ntile;
         const bool whole = (clo == 0 && chi == kTile);
         const uint32_t eb = empty0 + 8u * s;
+        const int nseg = nown + 1;                 /* segment 0 = the row left open by the previous tile */
 
         if (nown <= 1) {
-            /* ---- at most one row starts here: block reduction straight from registers */
+            /* ---- A: at most one row starts here: block reduction straight from registers */
             double sc = 0.0, so = 0.0;
             if (!whole) {
                 /* partial tile (first / last of a segment): mask explicitly, the slot may hold
                  * other segments' entries or stale data outside [lo,hi) */
 #pragma unroll
                 for (int i = 0; i < kIPT; ++i) {
-                    const int e = i * kConsumers + t;
+                    const int e = e0 + 32 * i;
                     if (e >= clo && e < chi) {
                         const double pr = S.val[e] * xv[i];
                         if (e < lsplit) sc += pr; else so += pr;
@@ -255,14 +261,14 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
                 double s1 = 0.0;
 #pragma unroll
                 for (int i = 0; i < kIPT; i += 2) {
-                    sc = fma(S.val[i * kConsumers + t], xv[i], sc);
-                    s1 = fma(S.val[(i + 1) * kConsumers + t], xv[i + 1], s1);
+                    sc = fma(S.val[e0 + 32 * i], xv[i], sc);
+                    s1 = fma(S.val[e0 + 32 * (i + 1)], xv[i + 1], s1);
                 }
                 sc += s1;
             } else {
 #pragma unroll
                 for (int i = 0; i < kIPT; ++i) {
-                    const int e = i * kConsumers + t;
+                    const int e = e0 + 32 * i;
                     const double pr = S.val[e] * xv[i];
                     if (e < lsplit) sc += pr; else so += pr;
                 }
@@ -293,55 +299,148 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
                  * (< kStages tiles), which is what makes the R / barrier-id rings safe */
                 release_stage(eb, lane);
             }
+            s = sn; ph = phn;
+            continue;
+        }
+
+        /* ---- products of my chunk (registers) */
+        double p[kIPT];
+        if (whole) {
+#pragma unroll
+            for (int i = 0; i < kIPT; ++i) p[i] = S.val[e0 + 32 * i] * xv[i];
         } else {
-            /* ---- several rows: products in place over val, G lanes per row */
-            if (whole) {
 #pragma unroll
-                for (int i = 0; i < kIPT; ++i) S.val[i * kConsumers + t] *= xv[i];
-            } else {
-#pragma unroll
-                for (int i = 0; i < kIPT; ++i) {
-                    const int e = i * kConsumers + t;
-                    S.val[e] = (e >= clo && e < chi) ? S.val[e] * xv[i] : 0.0;
-                }
+            for (int i = 0; i < kIPT; ++i) {
+                const int e = e0 + 32 * i;
+                p[i] = (e >= clo && e < chi) ? S.val[e] * xv[i] : 0.0;
             }
-            const int nseg = nown + 1;
-            const int len = chi - clo;             /* mean segment length picks the lanes per row */
-            const int lg = len >= 128 * nseg ? 5 : len >= 64 * nseg ? 4 : len >= 32 * nseg ? 3
-                         : len >= 16 * nseg ? 2 : len >= 8 * nseg ? 1 : 0;
-            /* beta*y of the rows this lane will write: loaded now, used after the reduction,
-             * so the global-load latency hides behind the barrier and the row sums */
-            double yin[4] = {0.0, 0.0, 0.0, 0.0};
-            int ypre = 0;
-            if (a.beta != 0.0) {
-                const int G = 1 << lg, ngroups = kConsumers >> lg;
-                const int grp = t >> lg;
-                const bool lead = (t & (G - 1)) == 0;
-                ypre = min(4, (nseg + ngroups - 1) >> (8 - lg));
-                for (int rr = 0; rr < ypre; ++rr) {
-                    const int sg = rr * ngroups + grp;
-                    const int row = rs + sg - 1;
-                    double v = 0.0;
-                    if (lead && sg >= 1 && sg < nseg && row != a.skip_first && row != a.skip_last) v = a.y[row];
-                    if (rr == 0) yin[0] = v; else if (rr == 1) yin[1] = v; else if (rr == 2) yin[2] = v; else yin[3] = v;
-                }
+        }
+
+        /* ---- W: 2..30 rows start here (mean row >= ~64 nnz): each warp reduces the pieces of
+         * rows inside its own chunk from registers; pieces of rows that cross chunk borders meet
+         * in shared memory (WC = piece of the row open at the chunk start, WT = piece of the row
+         * that leaves the chunk) and are summed in ascending chunk order after one barrier.
+         * Lane k holds boundary B(k): B(0) = 0, B(k) = start of owned row k-1 / end of the last. */
+        bool modeW = false;
+        int Bk = 0x7fffffff;
+        if (nseg <= 31 && S.rp_ok) {
+            const int T0 = base + clo, T1 = base + chi;
+            if (lane == 0) Bk = 0;
+            else if (lane <= nseg) Bk = min(max(S.rp[S.rp_off + lane - 1], T0), T1) - base;
+            const int Bn = __shfl_down_sync(kFull, Bk, 1);
+            const bool empty_row = lane >= 1 && lane < nseg && Bk == Bn;   /* empty rows: leave to path S */
+            modeW = __ballot_sync(kFull, empty_row) == 0u;
+        }
+        if (modeW) {
+            /* beta*y of the rows of this tile, one per lane, loaded before the sums */
+            double Yk = 0.0;
+            if (a.beta != 0.0 && lane >= 1 && lane <= nown) {
+                const int row = rs + lane - 1;
+                if (row != a.skip_first && row != a.skip_last) Yk = a.y[row];
             }
             if (has_next) {
                 mbar_wait(full0 + 8u * sn, phn);
                 gather(st[sn], base + step);
             }
-            named_bar_sync(bar_id, kConsumers);
-            switch (lg) {
-            case 5: reduce_rows<32>(a, S, j, t, base, clo, chi, rs, nown, ext, yin, ypre); break;
-            case 4: reduce_rows<16>(a, S, j, t, base, clo, chi, rs, nown, ext, yin, ypre); break;
-            case 3: reduce_rows<8>(a, S, j, t, base, clo, chi, rs, nown, ext, yin, ypre); break;
-            case 2: reduce_rows<4>(a, S, j, t, base, clo, chi, rs, nown, ext, yin, ypre); break;
-            case 1: reduce_rows<2>(a, S, j, t, base, clo, chi, rs, nown, ext, yin, ypre); break;
-            default: reduce_rows<1>(a, S, j, t, base, clo, chi, rs, nown, ext, yin, ypre); break;
+            const int c1 = c0 + kChunk;
+            const unsigned inb = (lane >= 1 && lane <= nseg) ? 1u : 0u;
+            int sg = __popc(__ballot_sync(kFull, inb && Bk <= c0));       /* segment open at c0 */
+            int sg_last = __popc(__ballot_sync(kFull, inb && Bk < c1));   /* segment holding c1-1 */
+            if (sg_last > nown) sg_last = nown;
+            double *WC = red + (kStages * 2 * kCWarps) + s * (3 * kCWarps);   /* [WC | WCend | WT] x 8 */
+            double wc = 0.0, wt = 0.0;
+            int wc_end = 1, wt_sg = -1;
+            for (; sg <= sg_last; ++sg) {
+                const int Bs = __shfl_sync(kFull, Bk, sg), Be = __shfl_sync(kFull, Bk, sg + 1);
+                const int sb = max(Bs, c0), se = min(Be, c1);
+                double acc = 0.0;
+#pragma unroll
+                for (int i = 0; i < kIPT; ++i)
+                    if ((unsigned)(e0 + 32 * i - sb) < (unsigned)(se - sb)) acc += p[i];
+                acc = warp_sum(acc);
+                const bool starts = sg >= 1 && Bs >= c0;
+                const bool ends = Be <= c1 && !(sg == nown && ext);
+                if (!starts) { wc = acc; wc_end = ends ? 1 : 0; }
+                else if (!ends) { wt = acc; wt_sg = sg; }
+                if (starts && ends) {
+                    const double yv = __shfl_sync(kFull, Yk, sg);
+                    if (lane == 0) emit_seg(a, j, sg, nown, false, rs, acc, yv);
+                }
             }
-            fence_proxy_async_smem();              /* generic writes to the slot before the next bulk copy */
+            if (lane == 0) {
+                WC[warp] = wc;
+                WC[kCWarps + warp] = (double)wc_end;
+                WC[2 * kCWarps + warp] = wt;
+            }
+            named_bar_sync(bar_id, kConsumers);
+            /* finish the row that left my chunk: WT + following chunks' WC, in chunk order */
+            const double ywt = __shfl_sync(kFull, Yk, wt_sg < 0 ? 0 : wt_sg);
+            if (lane == 0) {
+                if (wt_sg >= 0) {
+                    double tot = wt;
+                    bool closed = false;
+                    for (int w = warp + 1; w < kCWarps; ++w) {
+                        tot += WC[w];
+                        if (WC[kCWarps + w] != 0.0) { closed = true; break; }
+                    }
+                    if (closed) emit_seg(a, j, wt_sg, nown, false, rs, tot, ywt);
+                    else a.tail[j] = tot;                      /* the row leaves the tile (ext) */
+                }
+                if (warp == 0) {
+                    double tot = 0.0;                          /* the row left open by the previous tile */
+                    for (int w = 0; w < kCWarps; ++w) {
+                        tot += WC[w];
+                        if (WC[kCWarps + w] != 0.0) break;
+                    }
+                    a.carry[j] = tot;
+                }
+            }
+            /* released only now: the WC ring slot of this stage is reused when the stage is,
+             * so nobody may get 3 tiles ahead of a warp that still reads it */
             release_stage(eb, lane);
+            s = sn; ph = phn;
+            continue;
         }
+
+        /* ---- S: many short rows (or empty rows): products to shared memory in place over val,
+         * then G lanes per row */
+#pragma unroll
+        for (int i = 0; i < kIPT; ++i) S.val[e0 + 32 * i] = p[i];
+        const int len = chi - clo;                 /* mean segment length picks the lanes per row */
+        const int lg = len >= 128 * nseg ? 5 : len >= 64 * nseg ? 4 : len >= 32 * nseg ? 3
+                     : len >= 16 * nseg ? 2 : len >= 8 * nseg ? 1 : 0;
+        /* beta*y of the rows this lane will write: loaded now, used after the reduction,
+         * so the global-load latency hides behind the barrier and the row sums */
+        double yin[4] = {0.0, 0.0, 0.0, 0.0};
+        int ypre = 0;
+        if (a.beta != 0.0) {
+            const int G = 1 << lg, ngroups = kConsumers >> lg;
+            const int grp = t >> lg;
+            const bool lead = (t & (G - 1)) == 0;
+            ypre = min(4, (nseg + ngroups - 1) >> (8 - lg));
+            for (int rr = 0; rr < ypre; ++rr) {
+                const int sg = rr * ngroups + grp;
+                const int row = rs + sg - 1;
+                double v = 0.0;
+                if (lead && sg >= 1 && sg < nseg && row != a.skip_first && row != a.skip_last) v = a.y[row];
+                if (rr == 0) yin[0] = v; else if (rr == 1) yin[1] = v; else if (rr == 2) yin[2] = v; else yin[3] = v;
+            }
+        }
+        if (has_next) {
+            mbar_wait(full0 + 8u * sn, phn);
+            gather(st[sn], base + step);
+        }
+        named_bar_sync(bar_id, kConsumers);
+        switch (lg) {
+        case 5: reduce_rows<32>(a, S, j, t, base, clo, chi, rs, nown, ext, yin, ypre); break;
+        case 4: reduce_rows<16>(a, S, j, t, base, clo, chi, rs, nown, ext, yin, ypre); break;
+        case 3: reduce_rows<8>(a, S, j, t, base, clo, chi, rs, nown, ext, yin, ypre); break;
+        case 2: reduce_rows<4>(a, S, j, t, base, clo, chi, rs, nown, ext, yin, ypre); break;
+        case 1: reduce_rows<2>(a, S, j, t, base, clo, chi, rs, nown, ext, yin, ypre); break;
+        default: reduce_rows<1>(a, S, j, t, base, clo, chi, rs, nown, ext, yin, ypre); break;
+        }
+        fence_proxy_async_smem();              /* generic writes to the slot before the next bulk copy */
+        release_stage(eb, lane);
         s = sn; ph = phn;
     }
 }

@@ -85,6 +85,9 @@ def test_random_shapes_each_kernel_family(kind, ipt, monkeypatch):
         "all_long": rng.integers(2000, 9000, size=40),
         "many_empty_then_one": np.concatenate([np.zeros(10000, np.int64), [5], np.zeros(9000, np.int64)]),
         "leading_trailing_empty": np.concatenate([[0, 0, 0], rng.integers(1, 50, size=500), [0, 0]]),
+        "medium_64_500": rng.integers(64, 500, size=600),
+        "medium_180": np.full(900, 180, np.int64),
+        "medium_with_gaps": np.concatenate([rng.integers(100, 400, size=200), [0, 0, 3000, 1, 0], rng.integers(150, 260, size=300)]),
         "rows_of_two": np.full(40000, 2, np.int64),
         "rows_of_one_and_empty": rng.integers(0, 2, size=30000),
     }
