@@ -241,6 +241,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--exchange", default="symm", choices=["symm", "nccl"],
+                    help="split-row exchange for N>1: fused P2P over symmetric memory, or an NCCL all-gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -289,12 +291,31 @@ def main():
     slots = plan.edge_slots
     edge = torch.zeros(max(slots, 1), dtype=torch.float64, device="cuda")
     table = torch.zeros(world * max(slots, 1), dtype=torch.float64, device="cuda")
-    if slots:
-        plan.bind_edge_table(edge.data_ptr())
+    exchange = "none"
+    if world > 1 and slots:
+        exchange = args.exchange
+        if exchange == "symm":
+            try:
+                import torch.distributed._symmetric_memory as symm
+                tw = world * slots
+                sbuf = symm.empty(2 * tw + 2 * world, dtype=torch.float64, device=torch.device("cuda", local))
+                sbuf.zero_()
+                hdl = symm.rendezvous(sbuf, dist.group.WORLD)
+                torch.cuda.synchronize()
+                dist.barrier()
+                plan.bind_peer_tables(list(hdl.buffer_ptrs), tw)
+            except Exception as ex:          # no peer mapping available: fall back to NCCL
+                if rank == 0:
+                    print("symmetric memory unavailable (%s); using NCCL all-gather" % ex, file=sys.stderr)
+                exchange = "nccl"
+        if exchange == "nccl":
+            plan.bind_edge_table(edge.data_ptr())
 
     def step():
         plan.execute_device(ALPHA, BETA)
-        if world > 1 and slots:
+        if exchange == "symm":
+            plan.exchange_merge(ALPHA, BETA)
+        elif exchange == "nccl":
             dist.all_gather_into_tensor(table, edge)
             plan.merge_gathered(table.data_ptr(), ALPHA, BETA)
 
@@ -421,7 +442,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["desc"], "name": args.workload, "m": m, "n": n, "nnz": nnz,
-                       "partition": "v1 nnz-balanced x%d" % world, "kernel": args.kernel, "alpha": ALPHA, "beta": BETA,
+                       "partition": "v1 nnz-balanced x%d" % world, "kernel": args.kernel, "exchange": exchange, "alpha": ALPHA, "beta": BETA,
                        "l2": "inputs (%.1f GB per step) far exceed the 126 MB L2; no flush" % (alg_total / 1e9)},
             "hbm_gbs": alg_total / (ms_step * 1e-3) / 1e9,
             "hbm_frac_of_8000": alg_total / (ms_step * 1e-3) / 1e9 / (8000.0 * world),
@@ -433,7 +454,7 @@ def main():
             "e2e": {"value": 2.0 * nnz / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
                     "api": "sblas_spmv_plan_upload + execute_device (+ edge all-gather/merge) + download on a resident plan"},
-            "gpu_launches": args.steps * (plan.launches + (1 if (world > 1 and slots) else 0)),
+            "gpu_launches": args.steps * (plan.launches + (2 if exchange == "symm" else 1 if exchange == "nccl" else 0)),
             "clocks": clocks, "parity_check": check,
         }
         if not args.no_cpu and world == 1:

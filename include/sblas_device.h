@@ -74,6 +74,23 @@ cudaError_t sblas_launch_spmv_segment(const sblas_seg_args *a, int kind, int ipt
 cudaError_t sblas_launch_edge_merge(const int *mrow, const int *mbeg, const double *const *msrc, int nmerge,
                                     double *y, double alpha, double beta, cudaStream_t s);
 
+/* Fused split-row exchange for one-process-per-GPU plans over peer-mapped (symmetric)
+ * memory, no host involvement and no NCCL call per product:
+ *   publish: copy this rank's outgoing partials straight into the OWNER ranks' tables over
+ *            NVLink (P2P stores), fence, then raise the owner's arrive flag (epoch counter);
+ *            waits for the owner's ack of epoch-2 first (tables are double buffered by parity)
+ *   merge:   spin until every contributing rank's arrive flag reached `epoch`, finish the
+ *            split rows from the local table in ascending segment order, ack the contributors.
+ * Buffer layout of every rank (8-byte words): table[2][table_words], arrive[world], ack[world]. */
+cudaError_t sblas_launch_edge_publish(const double *local_block, const int *out_slot, const int *out_owner,
+                                      const long long *out_off, int nout, const int *owners, int nowners,
+                                      void *const *peer_bases, long long table_words, int world, int my_rank,
+                                      unsigned long long epoch, cudaStream_t s);
+cudaError_t sblas_launch_edge_merge_wait(const int *mrow, const int *mbeg, const long long *msrc_off, int nmerge,
+                                         double *y, double alpha, double beta, const int *contrib, int ncontrib,
+                                         void *const *peer_bases, long long table_words, int world, int my_rank,
+                                         unsigned long long epoch, cudaStream_t s);
+
 /* device fill helpers used by the plan */
 cudaError_t sblas_launch_fill_f64(double *p, long long n, double v, cudaStream_t s);
 

@@ -162,6 +162,17 @@ int sblas_spmv_plan_bind_edge_table(sblas_spmv_plan *plan, double *device_block)
  * (kind: 1 host->device, 2 device->host, 3 device->device); returns the cudaError_t */
 int sblas_memcpy(void *dst, const void *src, unsigned long long bytes, int kind);
 int sblas_device_synchronize(void);
+/* Rank plans, fused exchange: every rank owns a peer-mapped buffer of
+ * 2*table_words + 2*world 8-byte words (zero-initialised; table_words >= world*edge_slots),
+ * e.g. from torch.distributed._symmetric_memory; peer_bases[r] is rank r's buffer as mapped in
+ * THIS process.  After binding, sblas_spmv_plan_execute_device writes split-row partials into
+ * the table and sblas_spmv_plan_exchange_merge does the whole exchange on the GPU (P2P stores
+ * + flags over NVLink, see include/sblas_device.h): no NCCL call, no host synchronisation. */
+int sblas_spmv_plan_bind_peer_tables(sblas_spmv_plan *plan, void *const *peer_bases, long long table_words);
+int sblas_spmv_plan_exchange_merge(sblas_spmv_plan *plan, double alpha, double beta);
+/* phase 1 = publish only, 2 = merge only (0 = both): lets tests step several rank plans that
+ * share one GPU without any kernel waiting on a kernel that has not been launched */
+int sblas_spmv_plan_exchange_merge_phase(sblas_spmv_plan *plan, double alpha, double beta, int phase);
 /* algorithmic bytes of one execute: 12*nnz + 4*(rows+1)
  * + 8*x_touched + 8*rows*(1 + [beta != 0]), summed over the plan's GPUs */
 double sblas_spmv_plan_alg_bytes(const sblas_spmv_plan *plan, int beta_nonzero, long long x_touched_per_gpu);

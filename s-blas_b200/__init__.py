@@ -100,6 +100,9 @@ def lib():
     L.sblas_spmv_plan_edge_slots.argtypes = [_vp]
     L.sblas_spmv_plan_merge_gathered.argtypes = [_vp, _vp, C.c_double, C.c_double]
     L.sblas_spmv_plan_bind_edge_table.argtypes = [_vp, _vp]
+    L.sblas_spmv_plan_bind_peer_tables.argtypes = [_vp, P(_vp), _LL]
+    L.sblas_spmv_plan_exchange_merge.argtypes = [_vp, C.c_double, C.c_double]
+    L.sblas_spmv_plan_exchange_merge_phase.argtypes = [_vp, C.c_double, C.c_double, C.c_int]
     L.sblas_spmv_plan_local_segments.argtypes = [_vp]
     L.sblas_spmv_plan_local_segment.argtypes = [_vp, C.c_int, P(_LL)]
     L.sblas_spmv_plan_merge_list.argtypes = [_vp, C.c_int, P(C.c_int), P(P(C.c_int)), P(P(C.c_int)), P(P(_LL))]
@@ -340,6 +343,18 @@ class Plan:
         mrow, mbeg, moff = C.POINTER(C.c_int)(), C.POINTER(C.c_int)(), C.POINTER(_LL)()
         assert lib().sblas_spmv_plan_merge_list(self._h, dev, C.byref(n), C.byref(mrow), C.byref(mbeg), C.byref(moff)) == 0
         return [(mrow[i], [int(moff[k]) for k in range(mbeg[i], mbeg[i + 1])]) for i in range(n.value)]
+
+    def bind_peer_tables(self, peer_ptrs, table_words):
+        """peer_ptrs[r] = rank r's exchange buffer as mapped here (2*table_words + 2*world words, zeroed)."""
+        arr = (_vp * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        rc = lib().sblas_spmv_plan_bind_peer_tables(self._h, arr, int(table_words))
+        if rc != 0:
+            raise RuntimeError("sblas_spmv_plan_bind_peer_tables rc=%d: %s" % (rc, last_error()))
+
+    def exchange_merge(self, alpha, beta, phase=0):
+        rc = lib().sblas_spmv_plan_exchange_merge_phase(self._h, alpha, beta, phase)
+        if rc != 0:
+            raise RuntimeError("sblas_spmv_plan_exchange_merge rc=%d: %s" % (rc, last_error()))
 
     def bind_edge_table(self, device_ptr):
         assert lib().sblas_spmv_plan_bind_edge_table(self._h, int(device_ptr)) == 0

@@ -45,6 +45,12 @@ struct sblas_spmv_plan {
     int nseg; sblas_seg *segs;
     sblas_dev *devs;
     const double *gather_base;
+    /* fused exchange over peer-mapped memory */
+    int peer_bound, nout, nowners, ncontrib;
+    unsigned long long epoch;
+    long long table_words;
+    double *my_base;
+    void **d_peer_bases; int *d_out_slot, *d_out_owner, *d_owners, *d_contrib; long long *d_out_off, *d_msrc_off;
 };
 
 void sblas_set_error(const char *fmt, const char *a, const char *b, int line);

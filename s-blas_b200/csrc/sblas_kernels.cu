@@ -307,6 +307,74 @@ __global__ void edge_merge_kernel(const int *__restrict__ mrow, const int *__res
     y[r] = out;
 }
 
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+/* one thread: the lists are a handful of entries (<= 2 per local segment) */
+__global__ void edge_publish_kernel(const double *local_block, const int *out_slot, const int *out_owner,
+                                    const long long *out_off, int nout, const int *owners, int nowners,
+                                    void *const *peer_bases, long long table_words, int world, int my_rank,
+                                    unsigned long long epoch)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int parity = (int)(epoch & 1ull);
+    unsigned long long *mine = reinterpret_cast<unsigned long long *>(peer_bases[my_rank]);
+    for (int k = 0; k < nowners; ++k) {
+        /* back-pressure: the owner must have consumed what we wrote two products ago */
+        const unsigned long long *ack = mine + 2 * table_words + world + owners[k];
+        while (ld_acquire_sys(ack) + 2ull < epoch) { }
+    }
+    for (int i = 0; i < nout; ++i) {
+        double *dst = reinterpret_cast<double *>(peer_bases[out_owner[i]]) + parity * table_words + out_off[i];
+        *reinterpret_cast<volatile double *>(dst) = *reinterpret_cast<const volatile double *>(local_block + out_slot[i]);
+    }
+    __threadfence_system();
+    for (int k = 0; k < nowners; ++k) {
+        unsigned long long *flag = reinterpret_cast<unsigned long long *>(peer_bases[owners[k]]) + 2 * table_words + my_rank;
+        st_release_sys(flag, epoch);
+    }
+}
+
+__global__ void edge_merge_wait_kernel(const int *__restrict__ mrow, const int *__restrict__ mbeg,
+                                       const long long *__restrict__ msrc_off, int nmerge, double *y, double alpha,
+                                       double beta, const int *contrib, int ncontrib, void *const *peer_bases,
+                                       long long table_words, int world, int my_rank, unsigned long long epoch)
+{
+    unsigned long long *mine = reinterpret_cast<unsigned long long *>(peer_bases[my_rank]);
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < ncontrib; ++k) {
+            const unsigned long long *flag = mine + 2 * table_words + contrib[k];
+            while (ld_acquire_sys(flag) < epoch) { }
+        }
+    }
+    __syncthreads();
+    const double *table = reinterpret_cast<const double *>(mine) + (long long)(epoch & 1ull) * table_words;
+    for (int i = threadIdx.x; i < nmerge; i += blockDim.x) {
+        double s = 0.0;
+        for (int k = mbeg[i]; k < mbeg[i + 1]; ++k) s += *reinterpret_cast<const volatile double *>(table + msrc_off[k]);
+        const int r = mrow[i];
+        double out = alpha * s;
+        if (beta != 0.0) out += beta * y[r];
+        y[r] = out;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        for (int k = 0; k < ncontrib; ++k) {
+            unsigned long long *ack = reinterpret_cast<unsigned long long *>(peer_bases[contrib[k]]) + 2 * table_words + world + my_rank;
+            st_release_sys(ack, epoch);
+        }
+    }
+}
+
 __global__ void fill_f64_kernel(double *p, long long n, double v)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -380,6 +448,29 @@ extern "C" cudaError_t sblas_launch_edge_merge(const int *mrow, const int *mbeg,
 {
     if (nmerge <= 0) return cudaSuccess;
     edge_merge_kernel<<<(nmerge + 127) / 128, 128, 0, s>>>(mrow, mbeg, msrc, nmerge, y, alpha, beta);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t sblas_launch_edge_publish(const double *local_block, const int *out_slot, const int *out_owner,
+                                                 const long long *out_off, int nout, const int *owners, int nowners,
+                                                 void *const *peer_bases, long long table_words, int world,
+                                                 int my_rank, unsigned long long epoch, cudaStream_t s)
+{
+    if (nout <= 0) return cudaSuccess;
+    edge_publish_kernel<<<1, 32, 0, s>>>(local_block, out_slot, out_owner, out_off, nout, owners, nowners, peer_bases,
+                                         table_words, world, my_rank, epoch);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t sblas_launch_edge_merge_wait(const int *mrow, const int *mbeg, const long long *msrc_off,
+                                                    int nmerge, double *y, double alpha, double beta,
+                                                    const int *contrib, int ncontrib, void *const *peer_bases,
+                                                    long long table_words, int world, int my_rank,
+                                                    unsigned long long epoch, cudaStream_t s)
+{
+    if (nmerge <= 0 && ncontrib <= 0) return cudaSuccess;
+    edge_merge_wait_kernel<<<1, 128, 0, s>>>(mrow, mbeg, msrc_off, nmerge, y, alpha, beta, contrib, ncontrib,
+                                             peer_bases, table_words, world, my_rank, epoch);
     return cudaGetLastError();
 }
 

@@ -127,6 +127,10 @@ void sblas_spmv_plan_destroy(sblas_spmv_plan *P)
 {
     if (!P) return;
     for (int d = 0; d < P->ndev; ++d) free_dev(&P->devs[d], P->dry);
+    if (P->peer_bound) {
+        cudaFree(P->d_peer_bases); cudaFree(P->d_out_slot); cudaFree(P->d_out_owner); cudaFree(P->d_out_off);
+        cudaFree(P->d_owners); cudaFree(P->d_contrib); cudaFree(P->d_msrc_off);
+    }
     free(P->devs); free(P->segs); free(P->parts); free(P->g_owner); free(P->g_local);
     free(P->g_lo); free(P->g_hi); free(P->g_sf); free(P->g_sl);
     free(P);
@@ -557,6 +561,9 @@ static int enqueue_segments(sblas_spmv_plan *P, int d, double alpha, double beta
     for (int s = D->seg_begin; s < D->seg_end; ++s) {
         sblas_seg *S = &P->segs[s];
         S->args.alpha = alpha; S->args.beta = beta;
+        if (P->peer_bound)       /* edges go straight into this product's half of the exchange table */
+            S->args.edge = P->my_base + (long long)((P->epoch + 1) & 1ull) * P->table_words +
+                           (long long)P->rank * (2 * P->max_local) + 2 * S->lidx;
         CU(sblas_launch_spmv_segment(&S->args, D->kind, D->ipt, 0, D->streams[S->stream]));
     }
     for (int c = 1; c < D->nstreams; ++c) {
@@ -761,6 +768,96 @@ const int *sblas_spmv_plan_rowptr(sblas_spmv_plan *P, int dev, int *count)
 void *sblas_spmv_plan_stream(sblas_spmv_plan *P, int dev) { return P->devs[dev].streams ? (void *)P->devs[dev].streams[0] : NULL; }
 double *sblas_spmv_plan_edge_ptr(sblas_spmv_plan *P, int dev) { return P->devs[dev].d_edge; }
 int sblas_spmv_plan_edge_slots(const sblas_spmv_plan *P) { return 2 * P->max_local; }
+
+/* ---- fused exchange over peer-mapped memory (one process per GPU) */
+int sblas_spmv_plan_bind_peer_tables(sblas_spmv_plan *P, void *const *peer_bases, long long table_words)
+{
+    int rc = 0;
+    if (!P->rank_mode || P->dry || !peer_bases) return -1;
+    sblas_dev *D = &P->devs[0];
+    const int W = P->world, slots = 2 * P->max_local;
+    if (table_words < (long long)W * slots) return -1;
+    int *out_slot = (int *)calloc((size_t)P->nseg + 1, sizeof(int));
+    int *out_owner = (int *)calloc((size_t)P->nseg + 1, sizeof(int));
+    long long *out_off = (long long *)calloc((size_t)P->nseg + 1, sizeof(long long));
+    int *owners = (int *)calloc((size_t)W + 1, sizeof(int));
+    int *contrib = (int *)calloc((size_t)W + 1, sizeof(int));
+    char *seen = (char *)calloc((size_t)W + 1, 1);
+    int nout = 0, nown = 0, ncon = 0;
+    for (int s = 0; s < P->nseg; ++s) {
+        const sblas_seg *S = &P->segs[s];
+        if (!P->g_sf[S->gidx]) continue;
+        const int orank = P->g_owner[row_owner_seg(P, S->gidx)];
+        if (orank == P->rank) continue;
+        out_slot[nout] = 2 * S->lidx;
+        out_owner[nout] = orank;
+        out_off[nout] = (long long)P->rank * slots + 2 * S->lidx;
+        ++nout;
+        if (!seen[orank]) { seen[orank] = 1; owners[nown++] = orank; }
+    }
+    memset(seen, 0, (size_t)W + 1);
+    for (int i = 0; i < D->nmsrc; ++i) {
+        const int r = (int)(D->h_msrc_off[i] / slots);
+        if (r != P->rank && !seen[r]) { seen[r] = 1; contrib[ncon++] = r; }
+    }
+    if (D->seg_begin >= 0 || 1) {
+        CU(cudaSetDevice(D->device >= 0 ? D->device : 0));
+        CU(cudaMalloc((void **)&P->d_peer_bases, (size_t)W * sizeof(void *)));
+        CU(cudaMemcpy(P->d_peer_bases, peer_bases, (size_t)W * sizeof(void *), cudaMemcpyHostToDevice));
+        CU(cudaMalloc((void **)&P->d_out_slot, (size_t)(nout + 1) * sizeof(int)));
+        CU(cudaMalloc((void **)&P->d_out_owner, (size_t)(nout + 1) * sizeof(int)));
+        CU(cudaMalloc((void **)&P->d_out_off, (size_t)(nout + 1) * sizeof(long long)));
+        CU(cudaMalloc((void **)&P->d_owners, (size_t)(nown + 1) * sizeof(int)));
+        CU(cudaMalloc((void **)&P->d_contrib, (size_t)(ncon + 1) * sizeof(int)));
+        CU(cudaMalloc((void **)&P->d_msrc_off, (size_t)(D->nmsrc + 1) * sizeof(long long)));
+        CU(cudaMemcpy(P->d_out_slot, out_slot, (size_t)nout * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(P->d_out_owner, out_owner, (size_t)nout * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(P->d_out_off, out_off, (size_t)nout * sizeof(long long), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(P->d_owners, owners, (size_t)nown * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(P->d_contrib, contrib, (size_t)ncon * sizeof(int), cudaMemcpyHostToDevice));
+        if (D->nmsrc > 0)
+            CU(cudaMemcpy(P->d_msrc_off, D->h_msrc_off, (size_t)D->nmsrc * sizeof(long long), cudaMemcpyHostToDevice));
+    }
+    P->nout = nout; P->nowners = nown; P->ncontrib = ncon;
+    P->my_base = (double *)peer_bases[P->rank];
+    P->table_words = table_words;
+    P->peer_bound = 1;
+    P->epoch = 0;
+fail:
+    free(out_slot); free(out_owner); free(out_off); free(owners); free(contrib); free(seen);
+    return rc;
+}
+
+/* publish this rank's split-row partials into their owners' tables and finish the rows this
+ * rank owns; both enqueued on the plan's stream, nothing waits on the host */
+int sblas_spmv_plan_exchange_merge(sblas_spmv_plan *P, double alpha, double beta)
+{
+    return sblas_spmv_plan_exchange_merge_phase(P, alpha, beta, 0);
+}
+
+/* phase 0: publish + merge (normal use); 1: publish only; 2: merge only.  The split form lets
+ * several rank plans that share ONE GPU (tests) be stepped without kernels waiting on each other. */
+int sblas_spmv_plan_exchange_merge_phase(sblas_spmv_plan *P, double alpha, double beta, int phase)
+{
+    int rc = 0;
+    if (!P->peer_bound) return -1;
+    sblas_dev *D = &P->devs[0];
+    CU(cudaSetDevice(D->device));
+    if (phase != 2) P->epoch += 1;
+    const int slots = 2 * P->max_local;
+    const double *local_block = P->my_base + (long long)(P->epoch & 1ull) * P->table_words + (long long)P->rank * slots;
+    cudaStream_t st = D->streams ? D->streams[0] : 0;
+    if (phase != 2)
+    CU(sblas_launch_edge_publish(local_block, P->d_out_slot, P->d_out_owner, P->d_out_off, P->nout, P->d_owners,
+                                 P->nowners, (void *const *)P->d_peer_bases, P->table_words, P->world, P->rank,
+                                 P->epoch, st));
+    if (D->seg_begin >= 0 && phase != 1)
+        CU(sblas_launch_edge_merge_wait(D->d_mrow, D->d_mbeg, P->d_msrc_off, D->nmerge, D->d_y, alpha, beta,
+                                        P->d_contrib, P->ncontrib, (void *const *)P->d_peer_bases, P->table_words,
+                                        P->world, P->rank, P->epoch, st));
+fail:
+    return rc;
+}
 
 int sblas_spmv_plan_bind_edge_table(sblas_spmv_plan *P, double *device_block)
 {

@@ -158,3 +158,46 @@ def test_rank_plans_emulate_multi_gpu_on_one_device(qh768):
             check_tol(y, want, bound, "rank plans version=%d world=%d" % (version, world))
             for p in plans:
                 p.destroy()
+
+
+def test_fused_peer_exchange_on_one_device(qh768):
+    """The NCCL-free exchange (P2P stores + epoch flags, edge_publish / edge_merge_wait kernels):
+    `world` rank plans on cuda:0 with ordinary device buffers standing in for the peer-mapped
+    tables.  Stepped in phases (all products, all publishes, all merges) so that no kernel
+    ever waits for a kernel that has not run; three products in a row exercise the parity
+    double-buffering and the ack back-pressure."""
+    import torch
+    rng = np.random.default_rng(31)
+    lens = np.array([3, 1, 50000, 2, 2, 9000, 1, 4, 4], np.int64)
+    rp2, col2, val2 = make_csr(rng, len(lens), 3000, lens)
+    for rp, col, val, n in ((qh768["rowptr"], qh768["col"], qh768["val"], qh768["n"]), (rp2, col2, val2, 3000)):
+        m, nnz = len(rp) - 1, int(rp[-1])
+        x = rng.uniform(0.5, 1.5, n)
+        for version, world, nb, q in ((sb.V1, 4, 0, 1), (sb.V1, 8, 0, 1), (sb.V2, 4, nnz // 13, 2)):
+            plans = [sb.Plan.create_rank(version, m, n, nnz, val, rp, col, world, r, 0, kernel=2, nb=nb, q=q)
+                     for r in range(world)]
+            slots = plans[0].edge_slots
+            tw = world * max(slots, 1)
+            bufs = [torch.zeros(2 * tw + 2 * world, dtype=torch.float64, device="cuda") for _ in range(world)]
+            for p in plans:
+                p.bind_peer_tables([b.data_ptr() for b in bufs], tw)
+            y = rng.standard_normal(m)
+            for it in range(3):
+                want = oracle.csr_spmv(rp, col, val, x, A, B, y)
+                bound = oracle.csr_spmv_bound(rp, col, val, x, A, B, y)
+                for p in plans:
+                    p.upload(x, y)
+                    p.execute_device(A, B, sync=True)
+                for p in plans:
+                    p.exchange_merge(A, B, phase=1)
+                sb.device_synchronize()
+                for p in plans:
+                    p.exchange_merge(A, B, phase=2)
+                sb.device_synchronize()
+                ynew = y.copy()
+                for p in plans:
+                    p.download(ynew)
+                check_tol(ynew, want, bound, "fused exchange version=%d world=%d product %d" % (version, world, it))
+                y = ynew
+            for p in plans:
+                p.destroy()
