@@ -77,6 +77,14 @@ def workload(name):
         m = 6_250_000
         return dict(m=m, n=50_000_000, row_len=two_block(m, m, 180, 180), cols_mode=sb.COLS_BANDRUN, band=1 << 20,
                     desc="diagnostic: 6.25M rows x 180 nnz, banded runs")
+    if name == "rows100":      # diagnostic: the short-row block of g1m alone (x12 rows to fill the GPU)
+        m = 10_500_000
+        return dict(m=m, n=1_000_000, row_len=two_block(m, m, 100, 100), cols_mode=sb.COLS_PREFIX, band=0,
+                    desc="diagnostic: 10.5M rows x 100 nnz, prefix columns")
+    if name == "rows9000":     # diagnostic: the long-row block of g1m alone
+        m = 125_000
+        return dict(m=m, n=1_000_000, row_len=two_block(m, m, 9000, 9000), cols_mode=sb.COLS_PREFIX, band=0,
+                    desc="diagnostic: 125,000 rows x 9,000 nnz, prefix columns")
     if name == "rows2":        # diagnostic: the short-row block of big50m alone
         m = 43_750_000
         return dict(m=m, n=50_000_000, row_len=two_block(m, m, 2, 2), cols_mode=sb.COLS_BANDRUN, band=1 << 20,

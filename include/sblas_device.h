@@ -27,7 +27,7 @@ typedef struct sblas_seg_args {
     double *carry;        /* [ntile] tile kernel: sum of the row left open by tile j-1     */
     double *tail;         /* [ntile] tile kernel: partial of a row that leaves tile j      */
     const int *tstart;    /* [ntile+1] first row that STARTS inside tile j                 */
-    const int *tmeta;     /* [4*ntile] per tile {rs, re, start of row rs (clamped), ext}   */
+    const int *tmeta;     /* [8*ntile] per tile {rs, re, start of rs, flags} + 8 x u16 q_w */
     double alpha, beta;
     int row_lo, row_hi;   /* rows of the segment, inclusive, GPU-local numbering           */
     int nz0, nz1;         /* nnz range [nz0, nz1), GPU-local numbering                     */
@@ -58,8 +58,9 @@ cudaError_t sblas_launch_rebase_rowptr(const long long *rp64, long long first_id
  * start of tile j (binary search per tile; replaces CSR5's tile pointer
  * generation, spmv/include/detail/cuda/format_cuda.h:21-42). */
 cudaError_t sblas_launch_tile_rows(const sblas_seg_args *a, int tile, int *tstart_out, cudaStream_t s);
-/* tmeta[4*j..] = {rs, re, clamp(rowptr[rs]) or tile end, last owned row leaves the tile}
- * from tstart and rowptr: everything a tile needs in one 16-byte load. */
+/* tmeta[8*j..] = {rs, re, clamp(rowptr[rs]) or tile end, flags (1: last row leaves the tile,
+ * 2: an empty row starts here)} followed by 8 x uint16 "rows starting before chunk w":
+ * everything a tile needs in two 16-byte loads, computed once per plan. */
 cudaError_t sblas_launch_tile_meta(const sblas_seg_args *a, int tile, int *tmeta_out, cudaStream_t s);
 
 /* y[row_lo..row_hi] = alpha*A_seg*x + beta*y for one segment. kind: SBLAS_K_*;

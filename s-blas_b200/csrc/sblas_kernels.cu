@@ -267,6 +267,11 @@ __global__ void tile_rows_kernel(const sblas_seg_args a, int tile, int *tstart)
     tstart[j] = out;
 }
 
+/* tmeta[2j]   = {rs, re, start of row rs clamped to the tile (tile end if no row starts),
+ *               flags: bit0 = the last row that starts here leaves the tile,
+ *                      bit1 = one of the rows that start here is empty}
+ * tmeta[2j+1] = 8 x uint16: q_w = how many of the tile's rows start before chunk w
+ *               (chunk = tile/8 consecutive entries, one per consumer warp)            */
 __global__ void tile_meta_kernel(const sblas_seg_args a, int tile, int4 *tmeta)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -275,12 +280,31 @@ __global__ void tile_meta_kernel(const sblas_seg_args a, int tile, int4 *tmeta)
     const int T0 = (int)max((long long)a.nz0, base);
     const int T1 = (int)min((long long)a.nz1, base + tile);
     const int rs = a.tstart[j], re = a.tstart[j + 1];
-    int start0 = T1, ext = 0;
+    int start0 = T1, flags = 0;
+    unsigned q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (re > rs) {
         start0 = min(max(__ldg(a.rowptr + rs), T0), T1);
-        ext = min(__ldg(a.rowptr + re), a.nz1) > T1;
+        if (min(__ldg(a.rowptr + re), a.nz1) > T1) flags |= 1;
+        int prev = __ldg(a.rowptr + rs);
+        for (int r = rs + 1; r <= re; ++r) {               /* empty rows among [rs, re) */
+            const int cur = __ldg(a.rowptr + r);
+            if (cur == prev) { flags |= 2; break; }
+            prev = cur;
+        }
+        const int chunk = tile / 8;
+        for (int w = 0; w < 8; ++w) {
+            const long long cpos = base + (long long)w * chunk;      /* first r in [rs,re) with start >= cpos */
+            int lo = rs, hi = re;
+            while (lo < hi) {
+                const int mid = lo + ((hi - lo) >> 1);
+                if ((long long)max(__ldg(a.rowptr + mid), T0) < cpos) lo = mid + 1; else hi = mid;
+            }
+            q[w] = (unsigned)min(lo - rs, 65535);
+        }
     }
-    tmeta[j] = make_int4(rs, re, start0, ext);
+    tmeta[2 * j] = make_int4(rs, re, start0, flags);
+    tmeta[2 * j + 1] = make_int4((int)(q[0] | (q[1] << 16)), (int)(q[2] | (q[3] << 16)), (int)(q[4] | (q[5] << 16)),
+                                 (int)(q[6] | (q[7] << 16)));
 }
 
 __global__ void rebase_rowptr_kernel(const long long *__restrict__ rp64, long long first_idx, int total,

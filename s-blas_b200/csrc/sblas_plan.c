@@ -361,7 +361,7 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
         if (dry) continue;
         cudaStream_t st = D->streams[0];
         if (D->kind != SBLAS_K_VECTOR) {
-            CU(cudaMalloc((void **)&D->d_tmeta, (size_t)(tiles_total + 1) * 4 * sizeof(int)));
+            CU(cudaMalloc((void **)&D->d_tmeta, (size_t)(tiles_total + 1) * 8 * sizeof(int)));
             CU(cudaMalloc((void **)&D->d_tstart, (size_t)(tiles_total + 1) * sizeof(int)));
             CU(cudaMalloc((void **)&D->d_carry, (size_t)(tiles_total + 1) * sizeof(double)));
             CU(cudaMalloc((void **)&D->d_tail, (size_t)(tiles_total + 1) * sizeof(double)));
@@ -374,12 +374,12 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
             a->edge = D->d_edge + 2 * S->lidx;
             if (D->kind != SBLAS_K_VECTOR) {
                 a->tstart = D->d_tstart + S->tile_off;
-                a->tmeta = D->d_tmeta + 4 * S->tile_off;
+                a->tmeta = D->d_tmeta + 8 * S->tile_off;
                 a->carry = D->d_carry + S->tile_off;
                 a->tail = D->d_tail + S->tile_off;
                 if (a->ntile > 0) {
                     CU(sblas_launch_tile_rows(a, TILE, D->d_tstart + S->tile_off, st));
-                    CU(sblas_launch_tile_meta(a, TILE, D->d_tmeta + 4 * S->tile_off, st));
+                    CU(sblas_launch_tile_meta(a, TILE, D->d_tmeta + 8 * S->tile_off, st));
                 }
             }
         }

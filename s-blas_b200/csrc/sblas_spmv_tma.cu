@@ -49,7 +49,8 @@ struct __align__(128) Stage {
     double val[kTile];
     int col[kTile];
     int rp[kRpCap];
-    int4 meta;       /* {rs, re, start of row rs clamped to the tile, last row leaves tile} */
+    int4 meta;       /* {rs, re, start of row rs clamped to the tile, flags (1: last row leaves, 2: empty rows)} */
+    int4 meta2;      /* 8 x uint16: rows of the tile that start before chunk w */
     int rp_off;      /* rp[rp_off + q] == rowptr[rs + q] */
     int rp_ok;       /* the row pointer slice was staged */
 };
@@ -156,13 +157,13 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
             const uint64_t pol = policy_evict_first();
             const int4 *tm = reinterpret_cast<const int4 *>(a.tmeta);
             int j = cta;
-            int4 mnext = make_int4(0, 0, 0, 0);
-            if (j < ntile) mnext = __ldg(tm + j);
+            int4 mnext = make_int4(0, 0, 0, 0), m2next = make_int4(0, 0, 0, 0);
+            if (j < ntile) { mnext = __ldg(tm + 2 * j); m2next = __ldg(tm + 2 * j + 1); }
             int s = 0;
             uint32_t ph = 0;
             for (; j < ntile; j += ncta) {
-                const int4 m = mnext;
-                if (j + ncta < ntile) mnext = __ldg(tm + j + ncta);
+                const int4 m = mnext, m2 = m2next;
+                if (j + ncta < ntile) { mnext = __ldg(tm + 2 * (j + ncta)); m2next = __ldg(tm + 2 * (j + ncta) + 1); }
                 mbar_wait(empty0 + 8u * s, ph ^ 1u);
                 const int base = (a.tile0 + j) * kTile;
                 const int cnt = min(kTile, a.nz_total - base);
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
                 const bool rp_ok = (m.y - m.x >= 2) && (rpn <= kRpCap);
                 const uint32_t rb = rp_ok ? (uint32_t)rpn * 4u : 0u;
                 st[s].meta = m;
+                st[s].meta2 = m2;
                 st[s].rp_off = m.x - rp0;
                 st[s].rp_ok = rp_ok ? 1 : 0;
                 const uint32_t sbase = smem0 + (uint32_t)(s * sizeof(Stage));
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
         uint32_t phn = ph;
         if (sn == kStages) { sn = 0; phn ^= 1u; }
         const int rs = m.x, nown = m.y - m.x;
-        const bool ext = m.w != 0;
+        const bool ext = (m.w & 1) != 0;
         const int clo = lo, chi = hi;              /* current tile's range (gather overwrites lo/hi) */
         const int lsplit = m.z - base;
         const int bar_id = 1 + s;
@@ -316,78 +318,138 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
             }
         }
 
-        /* ---- W: 2..30 rows start here (mean row >= ~64 nnz): each warp reduces the pieces of
-         * rows inside its own chunk from registers; pieces of rows that cross chunk borders meet
-         * in shared memory (WC = piece of the row open at the chunk start, WT = piece of the row
-         * that leaves the chunk) and are summed in ascending chunk order after one barrier.
-         * Lane k holds boundary B(k): B(0) = 0, B(k) = start of owned row k-1 / end of the last. */
-        bool modeW = false;
-        int Bk = 0x7fffffff;
-        if (nseg <= 31 && S.rp_ok) {
+        /* ---- M: several rows, none empty (the common case).  Merge-style segmented sum inside
+         * every warp's own 256-entry chunk, no block-wide product buffer:
+         *   1. the warp's products go through its OWN slice of the stage (in place over val, pair-
+         *      swizzled) so that lane l ends up with entries 8l..8l+7 of the chunk;
+         *   2. row starts inside the chunk are scattered as byte flags (in place over the col slice,
+         *      already consumed); the metadata gives the chunk's first/last starting row directly;
+         *   3. every lane walks its 8 entries (complete rows inside a lane are written at once),
+         *      one segmented scan over the lanes' open sums closes rows that span lanes;
+         *   4. pieces of rows that cross chunk borders meet in shared memory (WC = the row open at
+         *      the chunk start, WT = the row that leaves the chunk) and are summed in ascending
+         *      chunk order after the tile's one barrier. */
+        if ((m.w & 2) == 0) {
+            const unsigned short *qw = reinterpret_cast<const unsigned short *>(&S.meta2);
+            const unsigned qa = qw[warp];
+            const unsigned qb = warp == kCWarps - 1 ? (unsigned)nown : (unsigned)qw[warp + 1];
             const int T0 = base + clo, T1 = base + chi;
-            if (lane == 0) Bk = 0;
-            else if (lane <= nseg) Bk = min(max(S.rp[S.rp_off + lane - 1], T0), T1) - base;
-            const int Bn = __shfl_down_sync(kFull, Bk, 1);
-            const bool empty_row = lane >= 1 && lane < nseg && Bk == Bn;   /* empty rows: leave to path S */
-            modeW = __ballot_sync(kFull, empty_row) == 0u;
-        }
-        if (modeW) {
-            /* beta*y of the rows of this tile, one per lane, loaded before the sums */
-            double Yk = 0.0;
-            if (a.beta != 0.0 && lane >= 1 && lane <= nown) {
-                const int row = rs + lane - 1;
-                if (row != a.skip_first && row != a.skip_last) Yk = a.y[row];
+            double *cv = S.val + c0;
+            unsigned char *F = reinterpret_cast<unsigned char *>(S.col + c0);
+            /* 1. transposed, swizzled store */
+#pragma unroll
+            for (int i = 0; i < kIPT; ++i) {
+                const int L = 4 * i + (lane >> 3), k = (lane >> 1) & 3;
+                cv[2 * (4 * L + (k ^ ((L >> 1) & 3))) + (lane & 1)] = p[i];
+            }
+            /* 2. flags */
+            reinterpret_cast<unsigned long long *>(F)[lane] = 0ull;
+            __syncwarp();
+            {
+                const bool staged = S.rp_ok != 0;
+                const int *rpl = S.rp + S.rp_off;
+                for (unsigned q = qa + lane; q < qb; q += 32) {
+                    const int v = staged ? rpl[q] : __ldg(a.rowptr + rs + q);
+                    F[min(max(v, T0), T1) - base - c0] = 1;
+                }
+            }
+            /* y of the row that leaves my chunk and of the first rows my lane will close */
+            const int wt_row = rs + (int)qb - 1;
+            const bool has_y = a.beta != 0.0;
+            double ywt = 0.0;
+            if (has_y && lane == 0 && qb > qa && wt_row != a.skip_first && wt_row != a.skip_last) ywt = a.y[wt_row];
+            __syncwarp();
+            double v[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double2 d = *reinterpret_cast<const double2 *>(cv + 2 * (4 * lane + (k ^ ((lane >> 1) & 3))));
+                v[2 * k] = d.x; v[2 * k + 1] = d.y;
+            }
+            const unsigned long long fl = reinterpret_cast<const unsigned long long *>(F)[lane];
+            const int cnt = __popcll(fl);
+            int excl = cnt;                                     /* rows starting in lanes before mine */
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int tt = __shfl_up_sync(kFull, excl, d);
+                if (lane >= d) excl += tt;
+            }
+            excl -= cnt;
+            const int orow = rs + (int)qa - 1 + excl;           /* row open at the start of my 8 entries */
+            double yp0 = 0.0, yp1 = 0.0;
+            if (has_y && cnt > 0) {
+                if (orow >= rs && orow != a.skip_first && orow != a.skip_last) yp0 = a.y[orow];
+                if (cnt > 1 && orow + 1 != a.skip_first && orow + 1 != a.skip_last) yp1 = a.y[orow + 1];
             }
             if (has_next) {
                 mbar_wait(full0 + 8u * sn, phn);
                 gather(st[sn], base + step);
             }
-            const int c1 = c0 + kChunk;
-            const unsigned inb = (lane >= 1 && lane <= nseg) ? 1u : 0u;
-            int sg = __popc(__ballot_sync(kFull, inb && Bk <= c0));       /* segment open at c0 */
-            int sg_last = __popc(__ballot_sync(kFull, inb && Bk < c1));   /* segment holding c1-1 */
-            if (sg_last > nown) sg_last = nown;
-            double *WC = red + (kStages * 2 * kCWarps) + s * (3 * kCWarps);   /* [WC | WCend | WT] x 8 */
-            double wc = 0.0, wt = 0.0;
-            int wc_end = 1, wt_sg = -1;
-            for (; sg <= sg_last; ++sg) {
-                const int Bs = __shfl_sync(kFull, Bk, sg), Be = __shfl_sync(kFull, Bk, sg + 1);
-                const int sb = max(Bs, c0), se = min(Be, c1);
-                double acc = 0.0;
+            /* 3. lane walk */
+            double sum = 0.0, head = 0.0;
+            bool seen = false;
+            int row = orow;
 #pragma unroll
-                for (int i = 0; i < kIPT; ++i)
-                    if ((unsigned)(e0 + 32 * i - sb) < (unsigned)(se - sb)) acc += p[i];
-                acc = warp_sum(acc);
-                const bool starts = sg >= 1 && Bs >= c0;
-                const bool ends = Be <= c1 && !(sg == nown && ext);
-                if (!starts) { wc = acc; wc_end = ends ? 1 : 0; }
-                else if (!ends) { wt = acc; wt_sg = sg; }
-                if (starts && ends) {
-                    const double yv = __shfl_sync(kFull, Yk, sg);
-                    if (lane == 0) emit_seg(a, j, sg, nown, false, rs, acc, yv);
+            for (int k = 0; k < 8; ++k) {
+                if ((fl >> (8 * k)) & 1ull) {
+                    if (!seen) {
+                        head = sum; seen = true;
+                    } else {                                    /* a whole row inside my 8 entries */
+                        double yv = 0.0;
+                        if (has_y) yv = (row == orow + 1) ? yp1 : a.y[row];
+                        if (row == a.skip_first) a.edge[0] = sum;
+                        else if (row == a.skip_last) a.edge[1] = sum;
+                        else a.y[row] = a.alpha * sum + a.beta * yv;
+                    }
+                    ++row;
+                    sum = 0.0;
                 }
+                sum += v[k];
             }
+            const unsigned bmask = __ballot_sync(kFull, seen);
+            const unsigned lower = bmask & ((2u << lane) - 1u);
+            const int segs = lower ? 31 - __clz((int)lower) : 0;       /* lane where my open run starts */
+            double I = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double tt = __shfl_up_sync(kFull, I, d);
+                if (lane - d >= segs) I += tt;
+            }
+            double cin = __shfl_up_sync(kFull, I, 1);
+            if (lane == 0) cin = 0.0;
+            const double closed = cin + head;                    /* total of the row open at my start */
+            const bool started_here = (bmask & ((1u << lane) - 1u)) != 0u;
+            if (seen && started_here) {
+                if (orow == a.skip_first) a.edge[0] = closed;
+                else if (orow == a.skip_last) a.edge[1] = closed;
+                else a.y[orow] = a.alpha * closed + a.beta * yp0;
+            }
+            /* 4. chunk borders */
+            const double I31 = __shfl_sync(kFull, I, 31);
+            const int f = bmask ? __ffs((int)bmask) - 1 : 0;
+            const double wcv = __shfl_sync(kFull, closed, f);
+            double *WC = red + (kStages * 2 * kCWarps) + s * (3 * kCWarps);   /* [WC | WCend | WT] x 8 */
             if (lane == 0) {
-                WC[warp] = wc;
-                WC[kCWarps + warp] = (double)wc_end;
-                WC[2 * kCWarps + warp] = wt;
+                WC[warp] = bmask ? wcv : I31;
+                WC[kCWarps + warp] = bmask ? 1.0 : 0.0;
+                WC[2 * kCWarps + warp] = I31;
             }
             named_bar_sync(bar_id, kConsumers);
-            /* finish the row that left my chunk: WT + following chunks' WC, in chunk order */
-            const double ywt = __shfl_sync(kFull, Yk, wt_sg < 0 ? 0 : wt_sg);
             if (lane == 0) {
-                if (wt_sg >= 0) {
-                    double tot = wt;
-                    bool closed = false;
+                if (bmask) {                                     /* the row that left my chunk */
+                    double tot = I31;
+                    bool closed_in_tile = false;
                     for (int w = warp + 1; w < kCWarps; ++w) {
                         tot += WC[w];
-                        if (WC[kCWarps + w] != 0.0) { closed = true; break; }
+                        if (WC[kCWarps + w] != 0.0) { closed_in_tile = true; break; }
                     }
-                    if (closed) emit_seg(a, j, wt_sg, nown, false, rs, tot, ywt);
-                    else a.tail[j] = tot;                      /* the row leaves the tile (ext) */
+                    if (!closed_in_tile && !ext) closed_in_tile = true;      /* ends exactly at the tile end */
+                    if (!closed_in_tile) a.tail[j] = tot;
+                    else if (wt_row == a.skip_first) a.edge[0] = tot;
+                    else if (wt_row == a.skip_last) a.edge[1] = tot;
+                    else a.y[wt_row] = a.alpha * tot + a.beta * ywt;
                 }
                 if (warp == 0) {
-                    double tot = 0.0;                          /* the row left open by the previous tile */
+                    double tot = 0.0;                            /* the row left open by the previous tile */
                     for (int w = 0; w < kCWarps; ++w) {
                         tot += WC[w];
                         if (WC[kCWarps + w] != 0.0) break;
@@ -395,8 +457,8 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
                     a.carry[j] = tot;
                 }
             }
-            /* released only now: the WC ring slot of this stage is reused when the stage is,
-             * so nobody may get 3 tiles ahead of a warp that still reads it */
+            fence_proxy_async_smem();          /* generic writes to the slot before the next bulk copy */
+            /* released only now: the WC ring slot of this stage is reused when the stage is */
             release_stage(eb, lane);
             s = sn; ph = phn;
             continue;
