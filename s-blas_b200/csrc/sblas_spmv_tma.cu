@@ -375,10 +375,12 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
             }
             excl -= cnt;
             const int orow = rs + (int)qa - 1 + excl;           /* row open at the start of my 8 entries */
-            double yp0 = 0.0, yp1 = 0.0;
+            double yp0 = 0.0, yp1 = 0.0, yp2 = 0.0, yp3 = 0.0;
             if (has_y && cnt > 0) {
                 if (orow >= rs && orow != a.skip_first && orow != a.skip_last) yp0 = a.y[orow];
                 if (cnt > 1 && orow + 1 != a.skip_first && orow + 1 != a.skip_last) yp1 = a.y[orow + 1];
+                if (cnt > 2 && orow + 2 != a.skip_first && orow + 2 != a.skip_last) yp2 = a.y[orow + 2];
+                if (cnt > 3 && orow + 3 != a.skip_first && orow + 3 != a.skip_last) yp3 = a.y[orow + 3];
             }
             if (has_next) {
                 mbar_wait(full0 + 8u * sn, phn);
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
                         head = sum; seen = true;
                     } else {                                    /* a whole row inside my 8 entries */
                         double yv = 0.0;
-                        if (has_y) yv = (row == orow + 1) ? yp1 : a.y[row];
+                        if (has_y) yv = (row == orow + 1) ? yp1 : (row == orow + 2) ? yp2 : (row == orow + 3) ? yp3 : a.y[row];
                         if (row == a.skip_first) a.edge[0] = sum;
                         else if (row == a.skip_last) a.edge[1] = sum;
                         else a.y[row] = a.alpha * sum + a.beta * yv;
