@@ -33,6 +33,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALPHA, BETA = 0.8401877171547095, 0.39438292681909304      # the harness's ALPHA/BETA (glibc rand(), seed 1)
+if os.environ.get("SBLAS_BENCH_BETA"):                      # diagnostics only
+    BETA = float(os.environ["SBLAS_BENCH_BETA"])
 SEED = 20260318
 
 

@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsblas_spmv.so")
+LIB_PATH = os.environ.get("SBLAS_LIB") or os.path.join(_HERE, "lib", "libsblas_spmv.so")   # SBLAS_LIB: A/B builds
 
 BASELINE, V1, V2 = 0, 1, 2
 SRC_HOST, SRC_DEVICE_SHARD, LAYOUT_ONLY = 0, 1, 2
