@@ -224,25 +224,21 @@ __global__ void __launch_bounds__(kThreads, (IPT <= 8 ? 4 : 2)) spmv_tile_kernel
 }
 
 /* rows that leave their tile: y[r] = alpha*(tail[j] + carry[j+1] + ... ) + beta*y[r],
- * one warp per tile, fixed summation order (the CSR5 "calibrator" step,
+ * one thread per tile (the per-tile metadata says at once whether there is anything to do),
+ * fixed left-to-right summation order (the CSR5 "calibrator" step,
  * csr5_spmv_cuda.h:313-382, without atomics). */
 __global__ void __launch_bounds__(kThreads) spmv_tile_fixup(const sblas_seg_args a, int tile)
 {
-    const int j = (int)(((long long)blockIdx.x * kThreads + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * kThreads + threadIdx.x;
     if (j >= a.ntile) return;
-    const int rs = __ldg(a.tstart + j), re = __ldg(a.tstart + j + 1);
-    if (re == rs) return;
-    const int r = re - 1;
-    const long long T1 = min((long long)a.nz1, (long long)(a.tile0 + j + 1) * tile);
+    const int4 m = __ldg(reinterpret_cast<const int4 *>(a.tmeta) + 2 * j);
+    if ((m.w & 1) == 0) return;                       /* no row leaves this tile */
+    const int r = m.y - 1;
     const int e = min(__ldg(a.rowptr + r + 1), a.nz1);
-    if ((long long)e <= T1) return;
     const int jend = (e - 1) / tile - a.tile0;
-    double acc = 0.0;
-    for (int i = j + 1 + lane; i <= jend; i += 32) acc += a.carry[i];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(kFull, acc, off);
-    if (lane == 0) emit_row(a, r, a.tail[j] + acc);
+    double acc = a.tail[j];
+    for (int i = j + 1; i <= jend; ++i) acc += a.carry[i];
+    emit_row(a, r, acc);
 }
 
 /* ------------------------------------------------------------------ plan helpers */
@@ -420,9 +416,7 @@ cudaError_t launch_tile(const sblas_seg_args *a, cudaStream_t s)
         attr_done[dev] = true;
     }
     spmv_tile_kernel<IPT><<<a->ntile, kThreads, Cfg::kSmem, s>>>(*a);
-    const long long warps = a->ntile;
-    const int blocks = (int)((warps * 32 + kThreads - 1) / kThreads);
-    spmv_tile_fixup<<<blocks, kThreads, 0, s>>>(*a, Cfg::kTile);
+    spmv_tile_fixup<<<(a->ntile + kThreads - 1) / kThreads, kThreads, 0, s>>>(*a, Cfg::kTile);
     return cudaGetLastError();
 }
 
@@ -516,8 +510,7 @@ extern "C" cudaError_t sblas_launch_spmv_segment(const sblas_seg_args *a, int ki
     if (kind == SBLAS_K_TMA && nnz > 0 && a->ntile > 0) {
         cudaError_t e = sblas_launch_tma(a, s);
         if (e != cudaSuccess) return e;
-        const int blocks = (int)(((long long)a->ntile * 32 + kThreads - 1) / kThreads);
-        spmv_tile_fixup<<<blocks, kThreads, 0, s>>>(*a, sblas_tma_tile_size());
+        spmv_tile_fixup<<<(a->ntile + kThreads - 1) / kThreads, kThreads, 0, s>>>(*a, sblas_tma_tile_size());
         return cudaGetLastError();
     }
     if (kind == SBLAS_K_TILE && nnz > 0 && a->ntile > 0) {
