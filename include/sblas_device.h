@@ -41,7 +41,7 @@ typedef struct sblas_seg_args {
 
 /* kernel families (the `kernel` argument of the reference API maps onto these,
  * see sblas_plan.c) */
-enum { SBLAS_K_VECTOR = 1, SBLAS_K_TILE = 2, SBLAS_K_TMA = 3 };
+enum { SBLAS_K_VECTOR = 1, SBLAS_K_TILE = 2, SBLAS_K_TMA = 3, SBLAS_K_VECP = 4 };
 
 /* nnz per tile of the tile kernel for a given items-per-thread choice (kind TILE),
  * or of the TMA-pipelined kernel (kind TMA, ipt ignored) */

@@ -21,7 +21,7 @@ LIB_PATH = os.environ.get("SBLAS_LIB") or os.path.join(_HERE, "lib", "libsblas_s
 
 BASELINE, V1, V2 = 0, 1, 2
 SRC_HOST, SRC_DEVICE_SHARD, LAYOUT_ONLY = 0, 1, 2
-K_VECTOR, K_TILE, K_TMA = 1, 2, 3
+K_VECTOR, K_TILE, K_TMA, K_VECP = 1, 2, 3, 4
 COLS_PREFIX, COLS_BANDED, COLS_UNIFORM, COLS_CIRCUIT, COLS_BANDRUN = 0, 1, 2, 3, 4
 
 _LL = C.c_longlong

@@ -79,6 +79,88 @@ __global__ void __launch_bounds__(kThreads) spmv_vec_kernel(const sblas_seg_args
     if (live && lane == 0) emit_row(a, r, s);
 }
 
+/* ------------------------------------------------------------------ pipelined vector kernel
+ * Warp per row for MEDIUM rows (tens to a few thousand nnz), persistent and software-pipelined:
+ * a warp walks its rows (row_lo + w, + nwarps, ...) as a stream of chunks of 32*EPL entries and
+ * always has the NEXT chunk's val/col loads (and the next row's bounds and y) in flight while it
+ * gathers x and accumulates the current one.  The row structure is used directly, so there is no
+ * transpose / flag / scan work at all: ~60 warp instructions per 256 nnz. */
+template <int EPL>
+__global__ void __launch_bounds__(kThreads, 3) spmv_vecp_kernel(const sblas_seg_args a)
+{
+    constexpr int CH = 32 * EPL;
+    const int lane = threadIdx.x & 31;
+    const int nw = (gridDim.x * kThreads) >> 5;
+    const int gw = (blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const int nrows = a.row_hi - a.row_lo + 1;
+    if (gw >= nrows) return;
+    const double *__restrict__ xp = a.x;
+
+    auto bounds = [&](int r, int &lo, int &hi) {
+        lo = max(__ldg(a.rowptr + r), a.nz0);
+        hi = min(__ldg(a.rowptr + r + 1), a.nz1);
+    };
+    auto load_chunk = [&](int k, int hi, double (&v)[EPL], unsigned (&c)[EPL]) {
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+            const int idx = k + lane + 32 * i;
+            v[i] = 0.0; c[i] = 0u;
+            if (idx < hi) {
+                v[i] = __ldg(a.val + idx);            /* streamed once: coalesced 256 B per request */
+                c[i] = (unsigned)__ldg(a.col + idx);
+            }
+        }
+    };
+
+    int r = a.row_lo + gw, lo, hi;
+    bounds(r, lo, hi);
+    int rn = r + nw, lon = 0, hin = 0;
+    if (rn <= a.row_hi) bounds(rn, lon, hin);
+    double v[EPL];
+    unsigned c[EPL];
+    load_chunk(lo, hi, v, c);
+    const bool has_y = a.beta != 0.0;
+
+    while (true) {
+        double yv = 0.0;
+        if (has_y && lane == 0 && r != a.skip_first && r != a.skip_last) yv = a.y[r];
+        double acc = 0.0;
+        const bool more_rows = rn <= a.row_hi;
+        int k = lo;
+        do {
+            /* gather x for the chunk in registers */
+            double xv[EPL];
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) xv[i] = __ldg(xp + c[i]);      /* c == 0 for padding: harmless */
+            /* next chunk: rest of this row, else the first chunk of my next row */
+            const int kn = k + CH;
+            double v2[EPL];
+            unsigned c2[EPL];
+            if (kn < hi) load_chunk(kn, hi, v2, c2);
+            else if (more_rows) load_chunk(lon, hin, v2, c2);
+            else {
+#pragma unroll
+                for (int i = 0; i < EPL; ++i) { v2[i] = 0.0; c2[i] = 0u; }
+            }
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) acc = fma(v[i], xv[i], acc);   /* padding has v == 0 */
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) { v[i] = v2[i]; c[i] = c2[i]; }
+            k = kn;
+        } while (k < hi);
+        acc = sblas::warp_sum(acc);
+        if (lane == 0) {
+            if (r == a.skip_first) a.edge[0] = acc;
+            else if (r == a.skip_last) a.edge[1] = acc;
+            else a.y[r] = a.alpha * acc + a.beta * yv;
+        }
+        if (!more_rows) break;
+        r = rn; lo = lon; hi = hin;
+        rn += nw;
+        if (rn <= a.row_hi) bounds(rn, lon, hin);
+    }
+}
+
 /* ------------------------------------------------------------------ tile kernel */
 template <int IPT>
 struct TileCfg {
@@ -429,6 +511,21 @@ cudaError_t launch_vec(const sblas_seg_args *a, cudaStream_t s)
     return cudaGetLastError();
 }
 
+template <int EPL>
+cudaError_t launch_vecp(const sblas_seg_args *a, cudaStream_t s)
+{
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && sms[dev] == 0) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    const long long nrows = (long long)a->row_hi - a->row_lo + 1;
+    long long blocks = (nrows * 32 + kThreads - 1) / kThreads;
+    const long long cap = (long long)(dev < 64 && sms[dev] ? sms[dev] : 148) * 3;      /* persistent: 3 CTAs per SM */
+    if (blocks > cap) blocks = cap;
+    spmv_vecp_kernel<EPL><<<(unsigned)blocks, kThreads, 0, s>>>(*a);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 extern "C" int sblas_tile_size(int ipt) { return kThreads * ipt; }
@@ -507,6 +604,7 @@ extern "C" cudaError_t sblas_launch_spmv_segment(const sblas_seg_args *a, int ki
     const long long nrows = (long long)a->row_hi - a->row_lo + 1;
     if (nrows <= 0) return cudaSuccess;
     const long long nnz = (long long)a->nz1 - a->nz0;
+    if (kind == SBLAS_K_VECP) return ipt == 4 ? launch_vecp<4>(a, s) : launch_vecp<8>(a, s);
     if (kind == SBLAS_K_TMA && nnz > 0 && a->ntile > 0) {
         cudaError_t e = sblas_launch_tma(a, s);
         if (e != cudaSuccess) return e;

@@ -94,6 +94,7 @@ static void pick_kernel(int kernel, long long dev_nnz, int *kind, int *ipt)
     if (k && !strcmp(k, "vec")) *kind = SBLAS_K_VECTOR;
     if (k && !strcmp(k, "tile")) *kind = SBLAS_K_TILE;
     if (k && !strcmp(k, "tma")) *kind = SBLAS_K_TMA;
+    if (k && !strcmp(k, "vecp")) *kind = SBLAS_K_VECP;
     const int e = env_int("SBLAS_IPT", 0);
     if (e == 4 || e == 8 || e == 16) *ipt = e;
 }
@@ -360,7 +361,7 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
         }
         if (dry) continue;
         cudaStream_t st = D->streams[0];
-        if (D->kind != SBLAS_K_VECTOR) {
+        if (D->kind != SBLAS_K_VECTOR && D->kind != SBLAS_K_VECP) {
             CU(cudaMalloc((void **)&D->d_tmeta, (size_t)(tiles_total + 1) * 8 * sizeof(int)));
             CU(cudaMalloc((void **)&D->d_tstart, (size_t)(tiles_total + 1) * sizeof(int)));
             CU(cudaMalloc((void **)&D->d_carry, (size_t)(tiles_total + 1) * sizeof(double)));
@@ -372,7 +373,7 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
             a->val = D->d_val; a->col = D->d_col; a->rowptr = D->d_rowptr;
             a->x = D->d_x; a->y = D->d_y;
             a->edge = D->d_edge + 2 * S->lidx;
-            if (D->kind != SBLAS_K_VECTOR) {
+            if (D->kind != SBLAS_K_VECTOR && D->kind != SBLAS_K_VECP) {
                 a->tstart = D->d_tstart + S->tile_off;
                 a->tmeta = D->d_tmeta + 8 * S->tile_off;
                 a->carry = D->d_carry + S->tile_off;
@@ -911,7 +912,7 @@ int sblas_spmv_plan_launches(const sblas_spmv_plan *P)
         const sblas_dev *D = &P->devs[P->segs[s].dev];
         const sblas_seg_args *a = &P->segs[s].args;
         if (a->row_hi < a->row_lo) continue;
-        n += (D->kind != SBLAS_K_VECTOR && a->ntile > 0) ? 2 : 1;
+        n += (D->kind != SBLAS_K_VECTOR && D->kind != SBLAS_K_VECP && a->ntile > 0) ? 2 : 1;
     }
     for (int d = 0; d < P->ndev; ++d) if (P->devs[d].nmerge > 0) ++n;
     return n;

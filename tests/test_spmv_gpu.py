@@ -71,7 +71,7 @@ def test_generator_g200_and_g10000():
                          kernels=(1, 2) if n > 200 else (1, 2, 3), what="g %d" % n)
 
 
-@pytest.mark.parametrize("kind,ipt", [("vec", 16), ("tile", 4), ("tile", 8), ("tile", 16), ("tma", 16)])
+@pytest.mark.parametrize("kind,ipt", [("vec", 16), ("tile", 4), ("tile", 8), ("tile", 16), ("tma", 16), ("vecp", 4), ("vecp", 8)])
 def test_random_shapes_each_kernel_family(kind, ipt, monkeypatch):
     """Short rows, empty rows, long rows, rows much longer than a tile, unsorted/duplicate columns."""
     monkeypatch.setenv("SBLAS_KIND", kind)
@@ -201,3 +201,75 @@ def test_fused_peer_exchange_on_one_device(qh768):
                 y = ynew
             for p in plans:
                 p.destroy()
+
+
+def _device_synth_plan(m, n, lens, cols_mode, band, seed=7):
+    """A resident single-GPU plan over a synthetic matrix generated ON the device at a size
+    the oracle cannot check row by row; returns (plan, rp, keepalive)."""
+    import torch
+    rp = np.zeros(m + 1, np.int64)
+    np.cumsum(lens, out=rp[1:])
+    nnz = int(rp[-1])
+    d_val = torch.empty(nnz, dtype=torch.float64, device="cuda")
+    d_col = torch.empty(nnz, dtype=torch.int32, device="cuda")
+    d_rp = torch.from_numpy(rp).cuda()
+    sb.synth_fill_csr(d_rp.data_ptr(), 0, m, 0, nnz, n, cols_mode, band, seed, d_val.data_ptr(), d_col.data_ptr())
+    torch.cuda.synchronize()
+    plan = sb.Plan.create_rank(sb.V1, m, n, nnz, d_val.data_ptr(), rp, d_col.data_ptr(), 1, 0, 0, kernel=1,
+                               flags=sb.SRC_DEVICE_SHARD, keep=(d_val, d_col))
+    return plan, rp, (d_val, d_col, d_rp)
+
+
+def test_full_size_properties_on_device_generated_matrix():
+    """Size-independent properties at a size beyond the oracle's reach (~150M nnz, mixed row
+    lengths incl. rows of 2, 100 and 9,000 nnz): run-to-run bit reproducibility (no FP atomics),
+    linearity in x, the alpha/beta contract, and a sample of rows against the oracle."""
+    rng = np.random.default_rng(3)
+    lens = np.concatenate([np.full(10000, 9000, np.int64), np.full(400000, 100, np.int64),
+                           np.full(1000000, 2, np.int64), rng.integers(1, 300, size=200000)])
+    m = len(lens)
+    n = 1 << 20
+    plan, rp, keep = _device_synth_plan(m, n, lens, sb.COLS_BANDRUN, 1 << 16)
+    yptr, first, rows = plan.y_ptr()
+    assert (first, rows) == (0, m)
+
+    def run(x, y0, alpha, beta):
+        y = y0.copy()
+        plan.execute(alpha, x, beta, y)
+        return y
+
+    x1, x2 = rng.standard_normal(n), rng.standard_normal(n)
+    y0 = rng.standard_normal(m)
+    a1 = run(x1, y0, 1.0, 0.0)
+    assert (run(x1, y0, 1.0, 0.0) == a1).all(), "two runs must agree bit for bit"
+    a2 = run(x2, y0, 1.0, 0.0)
+    a12 = run(x1 + x2, y0, 1.0, 0.0)
+    scale = np.abs(a1) + np.abs(a2) + 1e-300
+    # |A|(|x1|+|x2|) >= |a1|+|a2|: linearity to a few ulps of the row bound
+    absb = run(np.abs(x1) + np.abs(x2), y0, 1.0, 0.0)       # not the bound itself, only an order of magnitude
+    assert (np.abs(a12 - (a1 + a2)) <= 1e-12 * (np.abs(absb) + scale) + 1e-9 * scale).all()
+    full = run(x1, y0, -0.75, 0.5)
+    assert np.allclose(full, -0.75 * a1 + 0.5 * y0, rtol=0, atol=1e-12 * (np.abs(a1) + np.abs(y0)).max())
+    # sampled rows against the oracle
+    d_val, d_col, _ = keep
+    pick = np.unique(np.concatenate([[0, 9999, 10000, m - 1], rng.integers(0, m, size=400)]))
+    for r in pick:
+        b, e = int(rp[r]), int(rp[r + 1])
+        vv, cc = np.empty(e - b), np.empty(e - b, np.int32)
+        if e > b:
+            sb.memcpy(vv, d_val.data_ptr() + 8 * b, 8 * (e - b), 2)
+            sb.memcpy(cc, d_col.data_ptr() + 4 * b, 4 * (e - b), 2)
+        lrp = np.array([0, e - b], np.int64)
+        want = oracle.csr_spmv(lrp, cc, vv, x1, -0.75, 0.5, y0[r:r + 1])[0]
+        bound = oracle.csr_spmv_bound(lrp, cc, vv, x1, -0.75, 0.5, y0[r:r + 1])[0]
+        assert abs(full[r] - want) <= 1e-12 * bound + 1e-300, r
+    plan.destroy()
+
+
+def test_versions_and_kernels_agree_on_generator_matrix():
+    """baseline, v1 and v2 (several task sizes / streams) and kernels 1-3 on `g 4000`: all within
+    the tolerance of the oracle and of each other (what the harness's Y/N column checks)."""
+    r, c, v, alpha, beta = oracle.gen_g(4000)
+    rp = oracle.coo_to_rowptr(4000, r)
+    x, y0 = np.ones(4000), np.zeros(4000)
+    run_all_versions(rp, c, v, x, alpha, beta, y0, gpu_counts(), kernels=(1, 2, 3), what="g 4000")
