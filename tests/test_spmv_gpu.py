@@ -273,3 +273,27 @@ def test_versions_and_kernels_agree_on_generator_matrix():
     rp = oracle.coo_to_rowptr(4000, r)
     x, y0 = np.ones(4000), np.zeros(4000)
     run_all_versions(rp, c, v, x, alpha, beta, y0, gpu_counts(), kernels=(1, 2, 3), what="g 4000")
+
+
+def test_device_row_pointer_is_the_reference_local_row_pointer(qh768):
+    """The int32 row pointer a GPU works on is built ON the GPU from the int64 slice
+    (rebase_rowptr_kernel); it must equal, entry for entry, the local row pointer the reference
+    builds on the host for the same shard (dspmv_mgpu_v1.cu:125-133, dspmv_mgpu_baseline.cu:82-85)."""
+    rp, col, val = qh768["rowptr"], qh768["col"], qh768["val"]
+    m, n, nnz = qh768["m"], qh768["n"], qh768["nnz"]
+    for world in (1, 2, 4, 8):
+        parts = oracle.partition_v1(rp, world)
+        bparts = oracle.partition_baseline(rp, world)
+        for r in range(world):
+            for version in (sb.V1, sb.BASELINE):
+                p = sb.Plan.create_rank(version, m, n, nnz, val, rp, col, world, r, 0, kernel=2)
+                ptr, cnt = p.rowptr_ptr()
+                got = np.zeros(cnt, np.int32)
+                sb.memcpy(got, ptr, 4 * cnt, 2)
+                if version == sb.V1:
+                    want = oracle.local_rowptr_v1(rp, parts["start_idx"][r], parts["start_row"][r],
+                                                  parts["dev_m"][r], parts["dev_nnz"][r])
+                else:
+                    want = oracle.local_rowptr_baseline(rp, bparts["start_row"][r], bparts["dev_m"][r])
+                assert cnt == len(want) and (got == want).all(), (world, r, version)
+                p.destroy()
