@@ -55,7 +55,9 @@ struct __align__(128) Stage {
     int rp_ok;       /* the row pointer slice was staged */
 };
 
-constexpr int kSmemBytes = kStages * (int)sizeof(Stage) + 2 * kStages * 8 + kStages * (2 + 3) * kCWarps * 8;
+constexpr int kRing = 4;                       /* partial-sum buffers / named-barrier ids: a warp is at most
+                                                  kStages tiles ahead of the slowest one, so 4 slots suffice */
+constexpr int kSmemBytes = kStages * (int)sizeof(Stage) + 2 * kStages * 8 + kRing * (2 + 3) * kCWarps * 8;
 
 __device__ __forceinline__ void release_stage(uint32_t empty_bar, int lane)
 {
@@ -207,6 +209,7 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
     double xv[kIPT];        /* its gathered x values        */
     int s = 0;
     uint32_t ph = 0;
+    unsigned it = 0;        /* tiles done by this CTA */
 
     auto gather = [&](const Stage &S, int b) {
         m = S.meta;
@@ -239,7 +242,8 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
         const bool ext = (m.w & 1) != 0;
         const int clo = lo, chi = hi;              /* current tile's range (gather overwrites lo/hi) */
         const int lsplit = m.z - base;
-        const int bar_id = 1 + s;
+        const int ring = (int)(it & (kRing - 1));
+        const int bar_id = 1 + ring;
         const bool has_next = j + ncta < ntile;
         const bool whole = (clo == 0 && chi == kTile);
         const uint32_t eb = empty0 + 8u * s;
@@ -275,14 +279,14 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
                     if (e < lsplit) sc += pr; else so += pr;
                 }
             }
-            if (warp != 0) release_stage(eb, lane);            /* slot fully consumed */
+            release_stage(eb, lane);                           /* slot fully consumed: every warp hands it back */
             if (has_next) {
                 mbar_wait(full0 + 8u * sn, phn);
                 gather(st[sn], base + step);                   /* in flight during the reduction */
             }
             sc = warp_sum(sc);
             if (nown != 0) so = warp_sum(so);
-            double *R = red + s * (2 * kCWarps);
+            double *R = red + ring * (2 * kCWarps);
             if (lane == 0) { R[warp] = sc; R[kCWarps + warp] = so; }
             if (warp != 0) {
                 asm volatile("bar.arrive %0, %1;" ::"r"(bar_id), "r"(kConsumers) : "memory");
@@ -297,11 +301,8 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
                         if (ext) a.tail[j] = o; else emit_row(a, rs, o);
                     }
                 }
-                /* warp 0 releases last: bounds how far the other warps can run ahead
-                 * (< kStages tiles), which is what makes the R / barrier-id rings safe */
-                release_stage(eb, lane);
             }
-            s = sn; ph = phn;
+            s = sn; ph = phn; ++it;
             continue;
         }
 
@@ -429,7 +430,7 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
             const double I31 = __shfl_sync(kFull, I, 31);
             const int f = bmask ? __ffs((int)bmask) - 1 : 0;
             const double wcv = __shfl_sync(kFull, closed, f);
-            double *WC = red + (kStages * 2 * kCWarps) + s * (3 * kCWarps);   /* [WC | WCend | WT] x 8 */
+            double *WC = red + (kRing * 2 * kCWarps) + ring * (3 * kCWarps);   /* [WC | WCend | WT] x 8 */
             if (lane == 0) {
                 WC[warp] = bmask ? wcv : I31;
                 WC[kCWarps + warp] = bmask ? 1.0 : 0.0;
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
             fence_proxy_async_smem();          /* generic writes to the slot before the next bulk copy */
             /* released only now: the WC ring slot of this stage is reused when the stage is */
             release_stage(eb, lane);
-            s = sn; ph = phn;
+            s = sn; ph = phn; ++it;
             continue;
         }
 
@@ -505,7 +506,7 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
         }
         fence_proxy_async_smem();              /* generic writes to the slot before the next bulk copy */
         release_stage(eb, lane);
-        s = sn; ph = phn;
+        s = sn; ph = phn; ++it;
     }
 }
 
