@@ -43,6 +43,11 @@ int sblas_spmv_mgpu_v2(int m, int n, long long nnz, double *alpha, double *csrVa
                        long long *csrRowPtr, int *csrColIndex, double *x, double *beta,
                        double *y, int ngpu, int kernel, long long nb, int copy_of_workspace);
 
+/* Optional plan cache of the one-shot entry points (environment SBLAS_PLAN_CACHE=1, off by
+ * default = reference semantics): repeated calls with the same host arrays reuse the resident
+ * shards and only move x and y.  Drop every cached plan (needed after editing csrVal in place). */
+void sblas_spmv_cache_clear(void);
+
 /* helpers of spmv/include/spmv_kernel.h:32-36 (spmv/src/spmv_helper.cu:16-39,41-48,51-76) */
 int sblas_get_row_from_index(int n, const long long *a, long long idx);
 double sblas_get_time(void);

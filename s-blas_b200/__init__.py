@@ -64,6 +64,7 @@ def lib():
             f = getattr(L, pre + name)
             f.argtypes = mg + extra
             f.restype = C.c_int
+    L.sblas_spmv_cache_clear.restype = None
     L.sblas_get_row_from_index.argtypes = [C.c_int, _vp, _LL]
     L.sblas_get_time.restype = C.c_double
     L.sblas_get_gpu_availble_mem.argtypes = [C.c_int]
@@ -173,6 +174,11 @@ def spMV_mgpu_v2(m, n, nnz, alpha, csrVal, csrRowPtr, csrColIndex, x, beta, y, n
                               _ptr(_host(csrColIndex, np.int32, "csrColIndex")),
                               _ptr(_host(x, np.float64, "x")), C.addressof(b),
                               _ptr(_host(y, np.float64, "y")), ngpu, kernel, int(nb), copy_of_workspace)
+
+
+def cache_clear():
+    """Drop the plans cached by the one-shot entry points (SBLAS_PLAN_CACHE=1)."""
+    lib().sblas_spmv_cache_clear()
 
 
 def get_row_from_index(n, a, idx):

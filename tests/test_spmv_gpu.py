@@ -297,3 +297,28 @@ def test_device_row_pointer_is_the_reference_local_row_pointer(qh768):
                     want = oracle.local_rowptr_baseline(rp, bparts["start_row"][r], bparts["dev_m"][r])
                 assert cnt == len(want) and (got == want).all(), (world, r, version)
                 p.destroy()
+
+
+def test_one_shot_plan_cache(qh768, monkeypatch):
+    """SBLAS_PLAN_CACHE=1: repeated one-shot calls on the same host arrays reuse the upload; a
+    different x / y / alpha / beta still gives the right answer; an in-place edit of csrVal is
+    picked up after cache_clear()."""
+    monkeypatch.setenv("SBLAS_PLAN_CACHE", "1")
+    rng = np.random.default_rng(41)
+    r, c, v, _, _ = oracle.gen_g(2000)
+    rp = oracle.coo_to_rowptr(2000, r)
+    v = v.copy()
+    for it in range(4):
+        x, y0 = rng.standard_normal(2000), rng.standard_normal(2000)
+        al, be = float(rng.uniform(0.1, 2)), float(rng.uniform(0.1, 2))
+        for fn, extra in ((sb.spMV_mgpu_v1, (1, 2)), (sb.spMV_mgpu_v2, (1, 2, len(v) // 4, 2)), (sb.spMV_mgpu_baseline, (1,))):
+            y = y0.copy()
+            assert fn(2000, 2000, len(v), al, v, rp, c, x, be, y, *extra) == 0, sb.last_error()
+            check_tol(y, oracle.csr_spmv(rp, c, v, x, al, be, y0), oracle.csr_spmv_bound(rp, c, v, x, al, be, y0), "cache it %d" % it)
+    v[1000:2000] *= 3.0                       # in-place edit in the middle: invisible to the fingerprint
+    sb.cache_clear()
+    x, y0 = rng.standard_normal(2000), rng.standard_normal(2000)
+    y = y0.copy()
+    assert sb.spMV_mgpu_v1(2000, 2000, len(v), 1.0, v, rp, c, x, 0.5, y, 1, 1) == 0
+    check_tol(y, oracle.csr_spmv(rp, c, v, x, 1.0, 0.5, y0), oracle.csr_spmv_bound(rp, c, v, x, 1.0, 0.5, y0), "after clear")
+    sb.cache_clear()
