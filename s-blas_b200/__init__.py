@@ -43,7 +43,7 @@ class SegArgs(C.Structure):
                 ("carry", _vp), ("tail", _vp), ("tstart", _vp), ("tmeta", _vp), ("alpha", C.c_double), ("beta", C.c_double),
                 ("row_lo", C.c_int), ("row_hi", C.c_int), ("nz0", C.c_int), ("nz1", C.c_int),
                 ("skip_first", C.c_int), ("skip_last", C.c_int), ("tile0", C.c_int), ("ntile", C.c_int),
-                ("nz_total", C.c_int), ("pad_", C.c_int)]
+                ("nz_total", C.c_int), ("mode", C.c_int)]
 
 
 _lib = None

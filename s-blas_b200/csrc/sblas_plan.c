@@ -355,6 +355,7 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
             a->tile0 = a->nz0 / TILE;
             a->ntile = (a->nz1 > a->nz0) ? (int)(((long long)a->nz1 - 1) / TILE - a->tile0 + 1) : 0;
             a->nz_total = D->nnz;
+            a->mode = env_int("SBLAS_TMA_MODE", 0);
             S->tile_off = tiles_total;
             tiles_total += a->ntile + 1;
             S->stream = S->lidx % D->nstreams;

@@ -319,6 +319,90 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
             }
         }
 
+        /* ---- W: medium rows (no chunk holds more than 8 row starts, none empty).  The row starts cut a
+         * warp's 256-entry chunk into at most 9 pieces.  The products never leave the registers: the
+         * warp walks its 8 slices of 32 consecutive entries, lanes add their product to the running
+         * piece, and a warp reduction closes a piece wherever a row starts -- no flags, no scan, no
+         * shared-memory round trip, and the stage goes back to the producer before the sums start.
+         * Piece 0 belongs to the row open at the chunk start, the last piece to the row that leaves
+         * the chunk; both meet the neighbours' pieces after the tile's one barrier, as in M. */
+        if ((m.w & 6) == 4 && (a.mode & 1) == 0) {
+            const unsigned short *qw = reinterpret_cast<const unsigned short *>(&S.meta2);
+            const int qa = qw[warp];
+            const int qb = warp == kCWarps - 1 ? nown : (int)qw[warp + 1];
+            const int k = qb - qa;                               /* row starts in my chunk (<= 8) */
+            /* lane l < k: chunk-local start of row rs+qa+l; other lanes: the chunk end */
+            int v = kChunk;
+            if (lane < k) {
+                const int r = S.rp_ok ? S.rp[S.rp_off + qa + lane] : __ldg(a.rowptr + rs + qa + lane);
+                v = min(max(r, base + clo), base + chi) - base - c0;
+            }
+            release_stage(eb, lane);                             /* the stage is not touched again */
+            /* lane l in [1,k] owns piece l = row rs+qa+l-1: its y comes in during the sums */
+            const int myrow = rs + qa + lane - 1;
+            double yv = 0.0;
+            if (a.beta != 0.0 && lane >= 1 && lane <= k && myrow != a.skip_first && myrow != a.skip_last)
+                yv = a.y[myrow];
+            if (has_next) {
+                mbar_wait(full0 + 8u * sn, phn);
+                gather(st[sn], base + step);
+            }
+            double mine = 0.0, acc = 0.0;
+            int cur = 0;
+            int nb = __shfl_sync(kFull, v, 0);                   /* next row start (chunk-local), 256 = none */
+#pragma unroll
+            for (int i = 0; i < kIPT; ++i) {
+                int lo_lane = 0;
+                while (nb < 32 * (i + 1)) {                      /* a row starts inside slice i */
+                    const int o = nb - 32 * i;
+                    if (lane >= lo_lane && lane < o) acc += p[i];
+                    const double tot = warp_sum(acc);
+                    if (lane == cur) mine = tot;
+                    acc = 0.0;
+                    lo_lane = o;
+                    ++cur;
+                    nb = __shfl_sync(kFull, v, cur);
+                }
+                if (lane >= lo_lane) acc += p[i];
+            }
+            {
+                const double tot = warp_sum(acc);                /* the piece that leaves the chunk: cur == k */
+                if (lane == k) mine = tot;
+            }
+            if (lane >= 1 && lane < k) {       /* rows that start and end inside my chunk */
+                if (myrow == a.skip_first) a.edge[0] = mine;
+                else if (myrow == a.skip_last) a.edge[1] = mine;
+                else a.y[myrow] = a.alpha * mine + a.beta * yv;
+            }
+            double *WC = red + (kRing * 2 * kCWarps) + ring * (3 * kCWarps);   /* [WC | WCend | WT] x 8 */
+            if (lane == 0) { WC[warp] = mine; WC[kCWarps + warp] = k > 0 ? 1.0 : 0.0; }
+            if (lane == k) WC[2 * kCWarps + warp] = mine;
+            named_bar_sync(bar_id, kConsumers);
+            if (k > 0 && lane == k) {          /* the row that left my chunk */
+                double tot = mine;
+                bool closed_in_tile = false;
+                for (int w = warp + 1; w < kCWarps; ++w) {
+                    tot += WC[w];
+                    if (WC[kCWarps + w] != 0.0) { closed_in_tile = true; break; }
+                }
+                if (!closed_in_tile && !ext) closed_in_tile = true;          /* ends exactly at the tile end */
+                if (!closed_in_tile) a.tail[j] = tot;
+                else if (myrow == a.skip_first) a.edge[0] = tot;
+                else if (myrow == a.skip_last) a.edge[1] = tot;
+                else a.y[myrow] = a.alpha * tot + a.beta * yv;
+            }
+            if (warp == 0 && lane == 0) {
+                double tot = 0.0;              /* the row left open by the previous tile */
+                for (int w = 0; w < kCWarps; ++w) {
+                    tot += WC[w];
+                    if (WC[kCWarps + w] != 0.0) break;
+                }
+                a.carry[j] = tot;
+            }
+            s = sn; ph = phn; ++it;
+            continue;
+        }
+
         /* ---- M: several rows, none empty (the common case).  Merge-style segmented sum inside
          * every warp's own 256-entry chunk, no block-wide product buffer:
          *   1. the warp's products go through its OWN slice of the stage (in place over val, pair-
@@ -330,7 +414,7 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
          *   4. pieces of rows that cross chunk borders meet in shared memory (WC = the row open at
          *      the chunk start, WT = the row that leaves the chunk) and are summed in ascending
          *      chunk order after the tile's one barrier. */
-        if ((m.w & 2) == 0) {
+        if ((m.w & 2) == 0 && (a.mode & 2) == 0) {
             const unsigned short *qw = reinterpret_cast<const unsigned short *>(&S.meta2);
             const unsigned qa = qw[warp];
             const unsigned qb = warp == kCWarps - 1 ? (unsigned)nown : (unsigned)qw[warp + 1];

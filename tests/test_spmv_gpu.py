@@ -99,6 +99,34 @@ def test_random_shapes_each_kernel_family(kind, ipt, monkeypatch):
         run_all_versions(rp, col, val, x, 2.0, 0.0, y0, (1,), kernels=(1,), what="%s/%s/%d beta=0" % (name, kind, ipt))
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_tma_kernel_reduction_paths(mode, monkeypatch):
+    """Every per-tile reduction path of the TMA kernel on the same inputs: 0 = production choice
+    (A long rows / W warp pieces / M merge / S block), 1 = W off, 2 = M replaced by S, 3 = both.
+    Shapes sit on the eligibility borders (<= 8 row starts per 256-entry chunk) and v2's small tasks
+    put partial tiles (masked ranges, split first/last rows) through each path."""
+    monkeypatch.setenv("SBLAS_KIND", "tma")
+    monkeypatch.setenv("SBLAS_TMA_MODE", str(mode))
+    rng = np.random.default_rng(100 + mode)
+    shapes = {
+        "border_24_48": rng.integers(24, 49, size=4000),
+        "border_30_34": rng.integers(30, 35, size=5000),
+        "rows_180": np.full(1500, 180, np.int64),
+        "rows_100": np.full(2500, 100, np.int64),
+        "medium_64_2000": rng.integers(64, 2001, size=300),
+        "short_then_medium": np.concatenate([rng.integers(1, 6, size=20000), rng.integers(100, 300, size=800)]),
+        "medium_with_long": np.concatenate([rng.integers(100, 300, size=500), [30000], rng.integers(40, 90, size=900)]),
+        "rows_256_aligned": np.full(1000, 256, np.int64),
+        "rows_2": np.full(60000, 2, np.int64),
+    }
+    for name, lens in shapes.items():
+        m, n = len(lens), 6151
+        rp, col, val = make_csr(rng, m, n, lens)
+        x, y0 = rng.standard_normal(n), rng.standard_normal(m)
+        run_all_versions(rp, col, val, x, -1.75, 0.625, y0, (1,), kernels=(1,), what="%s/mode %d" % (name, mode))
+        run_all_versions(rp, col, val, x, 2.0, 0.0, y0, (1,), kernels=(1,), what="%s/mode %d beta=0" % (name, mode))
+
+
 def test_row_spanning_many_segments():
     """A row longer than nnz/ngpu (v1) and than nb (v2): >= 3 segments share it."""
     rng = np.random.default_rng(17)
