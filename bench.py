@@ -87,6 +87,14 @@ def workload(name):
         m = 125_000
         return dict(m=m, n=1_000_000, row_len=two_block(m, m, 9000, 9000), cols_mode=sb.COLS_PREFIX, band=0,
                     desc="diagnostic: 125,000 rows x 9,000 nnz, prefix columns")
+    if name == "rows9000b":    # diagnostic: long rows with banded-run columns (x from L2, not L1)
+        m = 125_000
+        return dict(m=m, n=50_000_000, row_len=two_block(m, m, 9000, 9000), cols_mode=sb.COLS_BANDRUN, band=1 << 20,
+                    desc="diagnostic: 125,000 rows x 9,000 nnz, banded runs")
+    if name == "rows180p":     # diagnostic: rows of 180 with prefix columns (x from L1)
+        m = 6_250_000
+        return dict(m=m, n=1_000_000, row_len=two_block(m, m, 180, 180), cols_mode=sb.COLS_PREFIX, band=0,
+                    desc="diagnostic: 6.25M rows x 180 nnz, prefix columns")
     if name == "rows2":        # diagnostic: the short-row block of big50m alone
         m = 43_750_000
         return dict(m=m, n=50_000_000, row_len=two_block(m, m, 2, 2), cols_mode=sb.COLS_BANDRUN, band=1 << 20,

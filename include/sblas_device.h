@@ -60,7 +60,7 @@ cudaError_t sblas_launch_rebase_rowptr(const long long *rp64, long long first_id
  * generation, spmv/include/detail/cuda/format_cuda.h:21-42). */
 cudaError_t sblas_launch_tile_rows(const sblas_seg_args *a, int tile, int *tstart_out, cudaStream_t s);
 /* tmeta[8*j..] = {rs, re, clamp(rowptr[rs]) or tile end, flags (1: last row leaves the tile,
- * 2: an empty row starts here, 4: no warp chunk holds more than 8 row starts)} followed by 8 x uint16 "rows starting before chunk w":
+ * 2: an empty row starts here, 4: no warp chunk holds more than 7 row starts)} followed by 8 x uint16 "rows starting before chunk w":
  * everything a tile needs in two 16-byte loads, computed once per plan. */
 cudaError_t sblas_launch_tile_meta(const sblas_seg_args *a, int tile, int *tmeta_out, cudaStream_t s);
 

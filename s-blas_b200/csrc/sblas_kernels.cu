@@ -348,7 +348,7 @@ __global__ void tile_rows_kernel(const sblas_seg_args a, int tile, int *tstart)
 /* tmeta[2j]   = {rs, re, start of row rs clamped to the tile (tile end if no row starts),
  *               flags: bit0 = the last row that starts here leaves the tile,
  *                      bit1 = one of the rows that start here is empty,
- *                      bit2 = no chunk holds more than 8 row starts (warp-piece path)}
+ *                      bit2 = no chunk holds more than 7 row starts (warp-piece path)}
  * tmeta[2j+1] = 8 x uint16: q_w = how many of the tile's rows start before chunk w
  *               (chunk = tile/8 consecutive entries, one per consumer warp)            */
 __global__ void tile_meta_kernel(const sblas_seg_args a, int tile, int4 *tmeta)
@@ -382,7 +382,7 @@ __global__ void tile_meta_kernel(const sblas_seg_args a, int tile, int4 *tmeta)
         }
         int most = re - rs - (int)q[7];                    /* row starts of the fullest chunk */
         for (int w = 0; w < 7; ++w) most = max(most, (int)q[w + 1] - (int)q[w]);
-        if (most <= 8 && re - rs < 65535) flags |= 4;
+        if (most <= 7 && re - rs < 65535) flags |= 4;
     }
     tmeta[2 * j] = make_int4(rs, re, start0, flags);
     tmeta[2 * j + 1] = make_int4((int)(q[0] | (q[1] << 16)), (int)(q[2] | (q[3] << 16)), (int)(q[4] | (q[5] << 16)),

@@ -37,12 +37,28 @@ namespace {
 using namespace sblas;
 
 constexpr int kTile = 2048;                    /* nnz per tile */
-constexpr int kConsumers = 256;                /* consumer threads */
+constexpr int kConsumers = 256;                /* consumer threads of one group (one tile at a time) */
 constexpr int kCWarps = kConsumers / 32;
-constexpr int kThreadsTma = kConsumers + 32;   /* + one producer warp */
+constexpr int kGroups = 1;                     /* consumer groups per CTA, each on its own tile (3 groups on a
+                                                  7-stage ring, one CTA per SM, measured slower: every group holds
+                                                  two stages, which starves the ring) */
+#ifndef SBLAS_W_SHUFFLE
+#define SBLAS_W_SHUFFLE 0
+#endif
+#ifndef SBLAS_W_DEFER
+#define SBLAS_W_DEFER 0
+#endif
+#ifndef SBLAS_TMA_CTAS
+#define SBLAS_TMA_CTAS 2
+#endif
+#ifndef SBLAS_TMA_STAGES
+#define SBLAS_TMA_STAGES 3
+#endif
+constexpr int kCtasPerSm = SBLAS_TMA_CTAS;
+constexpr int kThreadsTma = kGroups * kConsumers + 32;   /* + one producer warp */
 constexpr int kIPT = kTile / kConsumers;       /* 8 products per consumer thread */
 constexpr int kRpCap = 1032;                   /* row-pointer ints staged per tile (x4) */
-constexpr int kStages = 3;
+constexpr int kStages = SBLAS_TMA_STAGES;
 constexpr int kChunk = kTile / kCWarps;             /* entries owned by one consumer warp */
 
 struct __align__(128) Stage {
@@ -55,9 +71,13 @@ struct __align__(128) Stage {
     int rp_ok;       /* the row pointer slice was staged */
 };
 
-constexpr int kRing = 4;                       /* partial-sum buffers / named-barrier ids: a warp is at most
-                                                  kStages tiles ahead of the slowest one, so 4 slots suffice */
-constexpr int kSmemBytes = kStages * (int)sizeof(Stage) + 2 * kStages * 8 + kRing * (2 + 3) * kCWarps * 8;
+constexpr int kRing = 8;                       /* partial-sum buffers / named-barrier ids / border mbarriers.  A warp
+                                                  is at most kStages tiles ahead of the slowest one and path W
+                                                  settles a tile's chunk borders during the NEXT tile: 8 slots */
+static_assert(kGroups * kRing < 16, "named barrier ids");
+constexpr int kRedDoubles = kRing * (2 + 3) * kCWarps;          /* per group */
+constexpr int kBarBytes = (2 * kStages + kGroups * kRing) * 8;  /* full[], empty[], border[] mbarriers */
+constexpr int kSmemBytes = kStages * (int)sizeof(Stage) + kBarBytes + kGroups * kRedDoubles * 8;
 
 __device__ __forceinline__ void release_stage(uint32_t empty_bar, int lane)
 {
@@ -130,16 +150,17 @@ __device__ __forceinline__ void reduce_rows(const sblas_seg_args &a, const Stage
     }
 }
 
-__global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_seg_args a)
+__global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const sblas_seg_args a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     Stage *st = reinterpret_cast<Stage *>(smem);
     const uint32_t smem0 = smem_u32(smem);
     const uint32_t full0 = smem0 + (uint32_t)(kStages * sizeof(Stage));    /* full[s]  = full0 + 8 s  */
     const uint32_t empty0 = full0 + 8u * kStages;                           /* empty[s] = empty0 + 8 s */
-    double *red = reinterpret_cast<double *>(smem + kStages * sizeof(Stage) + 16 * kStages);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, pw = tid >> 5, lane = tid & 31;
+    const int grp = pw / kCWarps, warp = pw % kCWarps;      /* consumer group, warp inside the group */
+    const uint32_t wcbar0 = empty0 + 8u * kStages + 8u * kRing * grp;       /* border[r] = wcbar0 + 8 r */
+    double *red = reinterpret_cast<double *>(smem + kStages * sizeof(Stage) + kBarBytes) + grp * kRedDoubles;
     const int ncta = gridDim.x, cta = blockIdx.x;
     const int ntile = a.ntile;
 
@@ -149,11 +170,12 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
             mbar_init(full0 + 8u * s, 1);
             mbar_init(empty0 + 8u * s, kCWarps);
         }
+        for (int r = 0; r < kGroups * kRing; ++r) mbar_init(empty0 + 8u * kStages + 8u * r, kCWarps);
         mbar_fence_init();
     }
     __syncthreads();
 
-    if (warp == kCWarps) {
+    if (pw == kGroups * kCWarps) {
         /* ------------------------------------------------------------ producer */
         if (lane == 0) {
             const uint64_t pol = policy_evict_first();
@@ -194,22 +216,23 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
     /* ---------------------------------------------------------------- consumers
      * Element i of a thread is tile-local index  warp*256 + i*32 + lane : every warp owns a
      * contiguous 256-entry chunk of the tile, lanes are stride-1 inside it. */
-    const int t = tid;
-    int j = cta;
+    const int t = tid - grp * kConsumers;         /* thread inside the group */
+    int j = cta + grp * ncta;                     /* the CTA's tiles cta, cta+ncta, ... go round the groups */
     if (j >= ntile) return;
     const double *__restrict__ xp = a.x;
     const int nz0 = a.nz0, nz1 = a.nz1;
     int base = (a.tile0 + j) * kTile;            /* GPU-local nnz index of the tile (fits int32) */
-    const int step = ncta * kTile;
+    const int jstep = kGroups * ncta;
+    const int step = jstep * kTile;
     const int c0 = warp * kChunk;                /* my warp's chunk [c0, c0 + 256) */
     const int e0 = c0 + lane;                    /* my element i is e0 + 32 i */
 
     int4 m;                 /* metadata of the current tile */
     int lo, hi;             /* its valid tile-local range   */
     double xv[kIPT];        /* its gathered x values        */
-    int s = 0;
+    int s = grp;            /* the CTA's n-th tile sits in stage n mod kStages */
     uint32_t ph = 0;
-    unsigned it = 0;        /* tiles done by this CTA */
+    unsigned it = 0;        /* tiles done by this group */
 
     auto gather = [&](const Stage &S, int b) {
         m = S.meta;
@@ -230,24 +253,61 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
         }
     };
 
-    mbar_wait(full0, 0u);
-    gather(st[0], base);
+    /* path W settles the chunk borders of a tile one tile later (no block barrier): what lane 4k of
+     * a warp (the row that left its chunk) and warp 0 (the row left open by the previous tile) need */
+    bool pend = false;
+    unsigned wpar = 0;       /* phase parity per border mbarrier */
+    int p_info = 0, p_j = 0, p_row = 0;          /* info = ring | parity << 3 | ext << 4 | k << 5 */
+    double p_mine = 0.0, p_yv = 0.0;
+    auto settle = [&](bool wait) {
+        const int p_ring = p_info & 7, p_k = p_info >> 5;
+        const bool p_ext = (p_info & 16) != 0;
+        if (wait) mbar_wait(wcbar0 + 8u * p_ring, (uint32_t)(p_info >> 3) & 1u);   /* all eight warps have posted their pieces */
+        const double *WC = red + (kRing * 2 * kCWarps) + p_ring * (3 * kCWarps);   /* [WC | WCend | WT] x 8 */
+        if (p_k > 0 && lane == 4 * p_k) {                       /* the row that left my chunk */
+            double tot = p_mine;
+            bool closed_in_tile = false;
+            for (int w = warp + 1; w < kCWarps; ++w) {
+                tot += WC[w];
+                if (WC[kCWarps + w] != 0.0) { closed_in_tile = true; break; }
+            }
+            if (!closed_in_tile && !p_ext) closed_in_tile = true;            /* ends exactly at the tile end */
+            if (!closed_in_tile) a.tail[p_j] = tot;
+            else if (p_row == a.skip_first) a.edge[0] = tot;
+            else if (p_row == a.skip_last) a.edge[1] = tot;
+            else a.y[p_row] = a.alpha * tot + a.beta * p_yv;
+        }
+        if (warp == 0 && lane == 0) {
+            double tot = 0.0;                                   /* the row left open by the previous tile */
+            for (int w = 0; w < kCWarps; ++w) {
+                tot += WC[w];
+                if (WC[kCWarps + w] != 0.0) break;
+            }
+            a.carry[p_j] = tot;
+        }
+        pend = false;
+    };
 
-    for (; j < ntile; j += ncta, base += step) {
+    mbar_wait(full0 + 8u * s, 0u);
+    gather(st[s], base);
+
+    for (; j < ntile; j += jstep, base += step) {
         Stage &S = st[s];
-        int sn = s + 1;
+        int sn = s + kGroups;
         uint32_t phn = ph;
-        if (sn == kStages) { sn = 0; phn ^= 1u; }
+        if (sn >= kStages) { sn -= kStages; phn ^= 1u; }
         const int rs = m.x, nown = m.y - m.x;
         const bool ext = (m.w & 1) != 0;
         const int clo = lo, chi = hi;              /* current tile's range (gather overwrites lo/hi) */
         const int lsplit = m.z - base;
         const int ring = (int)(it & (kRing - 1));
-        const int bar_id = 1 + ring;
-        const bool has_next = j + ncta < ntile;
+        const int bar_id = 1 + grp * kRing + ring;
+        const bool has_next = j + jstep < ntile;
         const bool whole = (clo == 0 && chi == kTile);
         const uint32_t eb = empty0 + 8u * s;
         const int nseg = nown + 1;                 /* segment 0 = the row left open by the previous tile */
+
+        if (pend && !((m.w & 6) == 4 && (a.mode & 1) == 0)) settle(true);   /* W tiles settle after their gather */
 
         if (nown <= 1) {
             /* ---- A: at most one row starts here: block reduction straight from registers */
@@ -319,35 +379,44 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
             }
         }
 
-        /* ---- W: medium rows (no chunk holds more than 8 row starts, none empty).  The row starts cut a
-         * warp's 256-entry chunk into at most 9 pieces.  The products never leave the registers: the
-         * warp walks its 8 slices of 32 consecutive entries, lanes add their product to the running
-         * piece, and a warp reduction closes a piece wherever a row starts -- no flags, no scan, no
-         * shared-memory round trip, and the stage goes back to the producer before the sums start.
-         * Piece 0 belongs to the row open at the chunk start, the last piece to the row that leaves
-         * the chunk; both meet the neighbours' pieces after the tile's one barrier, as in M. */
+        /* ---- W: medium rows (no chunk holds more than 7 row starts, none empty).  The row starts cut a
+         * warp's 256-entry chunk into at most 8 pieces.  The products never leave the registers: the
+         * warp walks its 8 slices of 32 consecutive entries, every lane adds its product to the
+         * running piece and parks its partial sum in the warp's scratch (P[piece][lane]) wherever a
+         * row starts; ONE transposed pass then finishes all pieces at once (lanes 4c..4c+3 sum piece
+         * c: 8 loads, a 3-level tree, 2 shuffles) -- no flags, no scan, no per-piece shuffle chain, and
+         * the stage goes back to the producer before the sums start.  Piece 0 belongs to the row open
+         * at the chunk start, the last piece to the row that leaves the chunk; they meet the
+         * neighbours' pieces in shared memory, and that is settled during the NEXT tile (settle(),
+         * an mbarrier the eight warps arrive on), so no warp ever waits for the slowest one here. */
         if ((m.w & 6) == 4 && (a.mode & 1) == 0) {
             const unsigned short *qw = reinterpret_cast<const unsigned short *>(&S.meta2);
             const int qa = qw[warp];
             const int qb = warp == kCWarps - 1 ? nown : (int)qw[warp + 1];
-            const int k = qb - qa;                               /* row starts in my chunk (<= 8) */
+            const int k = qb - qa;                               /* row starts in my chunk (<= 7) */
             /* lane l < k: chunk-local start of row rs+qa+l; other lanes: the chunk end */
             int v = kChunk;
             if (lane < k) {
                 const int r = S.rp_ok ? S.rp[S.rp_off + qa + lane] : __ldg(a.rowptr + rs + qa + lane);
                 v = min(max(r, base + clo), base + chi) - base - c0;
             }
+#if SBLAS_W_SHUFFLE
             release_stage(eb, lane);                             /* the stage is not touched again */
-            /* lane l in [1,k] owns piece l = row rs+qa+l-1: its y comes in during the sums */
-            const int myrow = rs + qa + lane - 1;
+#else
+            double *pieces = S.val + c0;                         /* scratch: my own (consumed) slice of val */
+#endif
+            /* piece c is finished by lanes 4c..4c+3; lane 4c, c in [1,k], owns row rs+qa+c-1 */
+            const int pc = lane >> 2;
+            const int myrow = rs + qa + pc - 1;
+            const bool owner = (lane & 3) == 0 && pc >= 1 && pc <= k;
             double yv = 0.0;
-            if (a.beta != 0.0 && lane >= 1 && lane <= k && myrow != a.skip_first && myrow != a.skip_last)
-                yv = a.y[myrow];
+            if (a.beta != 0.0 && owner && myrow != a.skip_first && myrow != a.skip_last) yv = a.y[myrow];
             if (has_next) {
                 mbar_wait(full0 + 8u * sn, phn);
                 gather(st[sn], base + step);
             }
-            double mine = 0.0, acc = 0.0;
+            if (pend) settle(true);                                  /* the previous tile's chunk borders */
+            double acc = 0.0, mine = 0.0;
             int cur = 0;
             int nb = __shfl_sync(kFull, v, 0);                   /* next row start (chunk-local), 256 = none */
 #pragma unroll
@@ -356,8 +425,11 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
                 while (nb < 32 * (i + 1)) {                      /* a row starts inside slice i */
                     const int o = nb - 32 * i;
                     if (lane >= lo_lane && lane < o) acc += p[i];
-                    const double tot = warp_sum(acc);
-                    if (lane == cur) mine = tot;
+#if SBLAS_W_SHUFFLE
+                    { const double tot = warp_sum(acc); if (pc == cur) mine = tot; }
+#else
+                    pieces[cur * 32 + lane] = acc;
+#endif
                     acc = 0.0;
                     lo_lane = o;
                     ++cur;
@@ -365,40 +437,46 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
                 }
                 if (lane >= lo_lane) acc += p[i];
             }
+#if SBLAS_W_SHUFFLE
+            { const double tot = warp_sum(acc); if (pc == cur) mine = tot; }
+#else
+            pieces[cur * 32 + lane] = acc;                       /* the piece that leaves the chunk: cur == k */
+            __syncwarp();
             {
-                const double tot = warp_sum(acc);                /* the piece that leaves the chunk: cur == k */
-                if (lane == k) mine = tot;
+                /* lane (c, q) takes elements 16h + 4q + ((c + e) & 3), e = 0..7, h = e >> 2: every load is
+                 * bank-conflict-free and the four lanes of a piece cover its 32 partial sums */
+                const double *Q = pieces + pc * 32 + 4 * (lane & 3);
+                double t[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) t[e] = Q[16 * (e >> 2) + ((pc + e) & 3)];
+                mine = ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+                mine += __shfl_xor_sync(kFull, mine, 1);
+                mine += __shfl_xor_sync(kFull, mine, 2);         /* pieces beyond k: unused garbage */
             }
-            if (lane >= 1 && lane < k) {       /* rows that start and end inside my chunk */
+            fence_proxy_async_smem();          /* generic writes to the slot before the next bulk copy */
+            release_stage(eb, lane);
+#endif
+            if (owner && pc < k) {             /* rows that start and end inside my chunk */
                 if (myrow == a.skip_first) a.edge[0] = mine;
                 else if (myrow == a.skip_last) a.edge[1] = mine;
                 else a.y[myrow] = a.alpha * mine + a.beta * yv;
             }
             double *WC = red + (kRing * 2 * kCWarps) + ring * (3 * kCWarps);   /* [WC | WCend | WT] x 8 */
             if (lane == 0) { WC[warp] = mine; WC[kCWarps + warp] = k > 0 ? 1.0 : 0.0; }
-            if (lane == k) WC[2 * kCWarps + warp] = mine;
+            if (lane == 4 * k) WC[2 * kCWarps + warp] = mine;
+#if SBLAS_W_DEFER
+            __syncwarp();
+            if (lane == 0) mbar_arrive(wcbar0 + 8u * ring);
+            pend = true;
+            p_info = ring | (int)((wpar >> ring) & 1u) << 3 | (ext ? 16 : 0) | k << 5;
+            wpar ^= 1u << ring;
+            p_j = j; p_row = myrow; p_mine = mine; p_yv = yv;
+#else
             named_bar_sync(bar_id, kConsumers);
-            if (k > 0 && lane == k) {          /* the row that left my chunk */
-                double tot = mine;
-                bool closed_in_tile = false;
-                for (int w = warp + 1; w < kCWarps; ++w) {
-                    tot += WC[w];
-                    if (WC[kCWarps + w] != 0.0) { closed_in_tile = true; break; }
-                }
-                if (!closed_in_tile && !ext) closed_in_tile = true;          /* ends exactly at the tile end */
-                if (!closed_in_tile) a.tail[j] = tot;
-                else if (myrow == a.skip_first) a.edge[0] = tot;
-                else if (myrow == a.skip_last) a.edge[1] = tot;
-                else a.y[myrow] = a.alpha * tot + a.beta * yv;
-            }
-            if (warp == 0 && lane == 0) {
-                double tot = 0.0;              /* the row left open by the previous tile */
-                for (int w = 0; w < kCWarps; ++w) {
-                    tot += WC[w];
-                    if (WC[kCWarps + w] != 0.0) break;
-                }
-                a.carry[j] = tot;
-            }
+            p_info = ring | (ext ? 16 : 0) | k << 5;
+            p_j = j; p_row = myrow; p_mine = mine; p_yv = yv;
+            settle(false);
+#endif
             s = sn; ph = phn; ++it;
             continue;
         }
@@ -592,6 +670,7 @@ __global__ void __launch_bounds__(kThreadsTma, 2) spmv_tma_kernel(const sblas_se
         release_stage(eb, lane);
         s = sn; ph = phn; ++it;
     }
+    if (pend) settle(true);                        /* the last tile's chunk borders */
 }
 
 int g_sm_count[64] = {0};
@@ -613,7 +692,7 @@ cudaError_t sblas_launch_tma(const sblas_seg_args *a, cudaStream_t s)
         if (e != cudaSuccess) return e;
         attr_done[dev] = true;
     }
-    int grid = 2 * g_sm_count[dev];
+    int grid = kCtasPerSm * g_sm_count[dev];
     if (grid > a->ntile) grid = a->ntile;
     spmv_tma_kernel<<<grid, kThreadsTma, kSmemBytes, s>>>(*a);
     return cudaGetLastError();

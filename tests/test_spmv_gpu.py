@@ -102,7 +102,7 @@ def test_random_shapes_each_kernel_family(kind, ipt, monkeypatch):
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_tma_kernel_reduction_paths(mode, monkeypatch):
     """Every per-tile reduction path of the TMA kernel on the same inputs: 0 = production choice
-    (A long rows / W warp pieces / M merge / S block), 1 = W off, 2 = M replaced by S, 3 = both.
+    (A long rows / W warp pieces / M merge / S block), bit 0 = W off, bit 1 = M replaced by S.
     Shapes sit on the eligibility borders (<= 8 row starts per 256-entry chunk) and v2's small tasks
     put partial tiles (masked ranges, split first/last rows) through each path."""
     monkeypatch.setenv("SBLAS_KIND", "tma")
