@@ -42,7 +42,7 @@ typedef struct sblas_seg_args {
 
 /* kernel families (the `kernel` argument of the reference API maps onto these,
  * see sblas_plan.c) */
-enum { SBLAS_K_VECTOR = 1, SBLAS_K_TILE = 2, SBLAS_K_TMA = 3, SBLAS_K_VECP = 4 };
+enum { SBLAS_K_VECTOR = 1, SBLAS_K_TILE = 2, SBLAS_K_TMA = 3, SBLAS_K_VECP = 4, SBLAS_K_SHORT = 5 };
 
 /* nnz per tile of the tile kernel for a given items-per-thread choice (kind TILE),
  * or of the TMA-pipelined kernel (kind TMA, ipt ignored) */
@@ -63,6 +63,12 @@ cudaError_t sblas_launch_tile_rows(const sblas_seg_args *a, int tile, int *tstar
  * 2: an empty row starts here, 4: no warp chunk holds more than 7 row starts)} followed by 8 x uint16 "rows starting before chunk w":
  * everything a tile needs in two 16-byte loads, computed once per plan. */
 cudaError_t sblas_launch_tile_meta(const sblas_seg_args *a, int tile, int *tmeta_out, cudaStream_t s);
+
+/* Row-length statistics per block of `rb` rows of a segment (rows row_lo .. row_lo+nrows-1):
+ * out_max[b] = longest row, out_ptr[b] = clamp(rowptr[first row of block], nz0, nz1).  The plan
+ * bins consecutive blocks into panels and picks a kernel per panel (adaptive row binning). */
+cudaError_t sblas_launch_row_block_stats(const int *rowptr, int row_lo, int nrows, int rb, int nz0, int nz1,
+                                         int *out_max, int *out_ptr, cudaStream_t s);
 
 /* y[row_lo..row_hi] = alpha*A_seg*x + beta*y for one segment. kind: SBLAS_K_*;
  * ipt: items per thread of the tile kernel (4, 8 or 16); lanes: lanes per row of

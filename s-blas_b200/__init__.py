@@ -118,6 +118,7 @@ def lib():
     L.sblas_launch_rebase_rowptr.argtypes = [_vp, _LL, C.c_int, _LL, _vp, _vp]
     L.sblas_launch_tile_rows.argtypes = [P(SegArgs), C.c_int, _vp, _vp]
     L.sblas_launch_tile_meta.argtypes = [P(SegArgs), C.c_int, _vp, _vp]
+    L.sblas_launch_row_block_stats.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]
     L.sblas_tile_size_kind.argtypes = [C.c_int, C.c_int]
     L.sblas_launch_spmv_segment.argtypes = [P(SegArgs), C.c_int, C.c_int, C.c_int, _vp]
     L.sblas_launch_edge_merge.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_double, C.c_double, _vp]

@@ -5,14 +5,21 @@
 #include "sblas_device.h"
 #include "sblas_spmv.h"
 
+/* one kernel launch: a panel of a segment (consecutive rows binned by their longest row) */
+typedef struct sblas_unit {
+    sblas_seg_args args;   /* the panel's rows and nnz range; edge rows only at the segment's ends */
+    int kind, ipt;         /* SBLAS_K_* chosen for the panel                     */
+    long long tile_off;    /* offset of its tile metadata in the GPU's arrays    */
+} sblas_unit;
+
 /* one live segment held by this process (a v1 shard, a v2 task, a baseline block) */
 typedef struct sblas_seg {
     int gidx;              /* index in the global partition (plan->parts)       */
     int dev;               /* index of the GPU inside the plan                  */
     int lidx;              /* index among that GPU's segments                   */
     int stream;            /* which of the GPU's q streams runs it              */
-    long long tile_off;    /* offset of its tile metadata in the GPU's arrays   */
-    sblas_seg_args args;
+    sblas_seg_args args;   /* the whole segment (rows, nnz range, edge rows)    */
+    int unit_begin, unit_end;   /* plan->units[unit_begin, unit_end): its panels in row order */
 } sblas_seg;
 
 /* one GPU of the plan: a contiguous resident nnz range and the rows it touches */
@@ -43,6 +50,7 @@ struct sblas_spmv_plan {
     int *g_owner, *g_local, *g_lo, *g_hi, *g_sf, *g_sl;
     int max_local;
     int nseg; sblas_seg *segs;
+    int nunits, cap_units; sblas_unit *units;
     sblas_dev *devs;
     const double *gather_base;
     /* fused exchange over peer-mapped memory */

@@ -79,6 +79,35 @@ __global__ void __launch_bounds__(kThreads) spmv_vec_kernel(const sblas_seg_args
     if (live && lane == 0) emit_row(a, r, s);
 }
 
+/* ------------------------------------------------------------------ short-row kernel
+ * Thread per row for panels whose rows all hold at most a handful of entries (the plan bins row
+ * blocks by their longest row).  Nothing to reduce across lanes and nothing to stage: every load
+ * of a thread is independent of its neighbours', 2048 threads per SM keep ~70 KB in flight, and
+ * the row pointer / y accesses of a warp are 128 / 256 contiguous bytes.  Rows of exactly two
+ * entries on an even offset take val and col as one 16-byte and one 8-byte load. */
+__global__ void __launch_bounds__(kThreads, 8) spmv_short_kernel(const sblas_seg_args a)
+{
+    const long long gid = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (gid > (long long)a.row_hi - a.row_lo) return;
+    const int r = a.row_lo + (int)gid;
+    const int lo = max(__ldg(a.rowptr + r), a.nz0);
+    const int hi = min(__ldg(a.rowptr + r + 1), a.nz1);
+    const bool edge = (r == a.skip_first) || (r == a.skip_last);
+    double yv = 0.0;
+    if (a.beta != 0.0 && !edge) yv = a.y[r];
+    double acc = 0.0;
+    if (hi - lo == 2 && (lo & 1) == 0) {
+        const double2 v = __ldg(reinterpret_cast<const double2 *>(a.val + lo));
+        const int2 c = __ldg(reinterpret_cast<const int2 *>(a.col + lo));
+        acc = fma(v.y, __ldg(a.x + c.y), v.x * __ldg(a.x + c.x));
+    } else {
+        for (int k = lo; k < hi; ++k) acc = fma(__ldg(a.val + k), __ldg(a.x + __ldg(a.col + k)), acc);
+    }
+    if (r == a.skip_first) a.edge[0] = acc;
+    else if (r == a.skip_last) a.edge[1] = acc;
+    else a.y[r] = a.alpha * acc + a.beta * yv;
+}
+
 /* ------------------------------------------------------------------ pipelined vector kernel
  * Warp per row for MEDIUM rows (tens to a few thousand nnz), persistent and software-pipelined:
  * a warp walks its rows (row_lo + w, + nwarps, ...) as a stream of chunks of 32*EPL entries and
@@ -389,6 +418,28 @@ __global__ void tile_meta_kernel(const sblas_seg_args a, int tile, int4 *tmeta)
                                  (int)(q[6] | (q[7] << 16)));
 }
 
+/* per block of `rb` consecutive rows: the longest row and the (clamped) row pointer at the block
+ * start -- what the plan needs to bin row panels by length (adaptive kernel choice per panel) */
+__global__ void row_block_stats_kernel(const int *__restrict__ rowptr, int row_lo, int nrows, int rb, int nz0, int nz1,
+                                       int *__restrict__ out_max, int *__restrict__ out_ptr)
+{
+    __shared__ int red[kThreads / 32];
+    const int b = blockIdx.x;
+    const int r0 = b * rb, r1 = min(r0 + rb, nrows);
+    int mx = 0;
+    for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x)
+        mx = max(mx, __ldg(rowptr + row_lo + r + 1) - __ldg(rowptr + row_lo + r));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(kFull, mx, off));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kThreads / 32; ++w) mx = max(mx, red[w]);
+        out_max[b] = mx;
+        out_ptr[b] = min(max(__ldg(rowptr + row_lo + r0), nz0), nz1);
+    }
+}
+
 __global__ void rebase_rowptr_kernel(const long long *__restrict__ rp64, long long first_idx, int total,
                                      long long count, int *__restrict__ out)
 {
@@ -562,6 +613,15 @@ extern "C" int sblas_tile_size_kind(int kind, int ipt)
     return kind == SBLAS_K_TMA ? sblas_tma_tile_size() : kThreads * ipt;
 }
 
+extern "C" cudaError_t sblas_launch_row_block_stats(const int *rowptr, int row_lo, int nrows, int rb, int nz0, int nz1,
+                                                    int *out_max, int *out_ptr, cudaStream_t s)
+{
+    const int nb = (nrows + rb - 1) / rb;
+    if (nb <= 0) return cudaSuccess;
+    row_block_stats_kernel<<<nb, kThreads, 0, s>>>(rowptr, row_lo, nrows, rb, nz0, nz1, out_max, out_ptr);
+    return cudaGetLastError();
+}
+
 extern "C" cudaError_t sblas_launch_edge_merge(const int *mrow, const int *mbeg, const double *const *msrc,
                                                int nmerge, double *y, double alpha, double beta, cudaStream_t s)
 {
@@ -609,6 +669,10 @@ extern "C" cudaError_t sblas_launch_spmv_segment(const sblas_seg_args *a, int ki
     if (nrows <= 0) return cudaSuccess;
     const long long nnz = (long long)a->nz1 - a->nz0;
     if (kind == SBLAS_K_VECP) return ipt == 4 ? launch_vecp<4>(a, s) : launch_vecp<8>(a, s);
+    if (kind == SBLAS_K_SHORT) {
+        spmv_short_kernel<<<(unsigned)((nrows + kThreads - 1) / kThreads), kThreads, 0, s>>>(*a);
+        return cudaGetLastError();
+    }
     if (kind == SBLAS_K_TMA && nnz > 0 && a->ntile > 0) {
         cudaError_t e = sblas_launch_tma(a, s);
         if (e != cudaSuccess) return e;

@@ -132,7 +132,7 @@ void sblas_spmv_plan_destroy(sblas_spmv_plan *P)
         cudaFree(P->d_peer_bases); cudaFree(P->d_out_slot); cudaFree(P->d_out_owner); cudaFree(P->d_out_off);
         cudaFree(P->d_owners); cudaFree(P->d_contrib); cudaFree(P->d_msrc_off);
     }
-    free(P->devs); free(P->segs); free(P->parts); free(P->g_owner); free(P->g_local);
+    free(P->devs); free(P->segs); free(P->units); free(P->parts); free(P->g_owner); free(P->g_local);
     free(P->g_lo); free(P->g_hi); free(P->g_sf); free(P->g_sl);
     free(P);
 }
@@ -212,11 +212,57 @@ static int row_owner_seg(const sblas_spmv_plan *P, int t)
     return o;
 }
 
+static sblas_unit *new_unit(sblas_spmv_plan *P)
+{
+    if (P->nunits == P->cap_units) {
+        const int cap = P->cap_units ? 2 * P->cap_units : 16;
+        sblas_unit *u = (sblas_unit *)realloc(P->units, (size_t)cap * sizeof(sblas_unit));
+        if (!u) return NULL;
+        P->units = u; P->cap_units = cap;
+    }
+    sblas_unit *U = &P->units[P->nunits++];
+    memset(U, 0, sizeof *U);
+    return U;
+}
+
+#define SBLAS_PANEL_ROWS 4096          /* rows per statistics block */
+#define SBLAS_PANEL_MAX 32             /* most panels per segment (else: one panel) */
+
+/* Adaptive row binning at plan level: cut a segment into panels of consecutive rows by the
+ * longest row of every 4096-row block (computed on the GPU): blocks whose rows all hold at most
+ * `short_max` entries go to the thread-per-row kernel, everything else to the GPU's general
+ * kernel (whose per-tile reduction adapts further).  Short runs below `min_nnz` entries are not
+ * worth a launch of their own and join their neighbours.  run_class/run_begin: outputs
+ * (run i covers blocks [run_begin[i], run_begin[i+1])); returns the number of runs. */
+static int bin_blocks(const int *bmax, const int *bptr, int nblk, int nz1, int short_max, long long min_nnz,
+                      int *run_class, int *run_begin)
+{
+    int nrun = 0;
+    for (int b = 0; b < nblk; ++b) {
+        const int cls = bmax[b] <= short_max;
+        if (nrun == 0 || run_class[nrun - 1] != cls) { run_class[nrun] = cls; run_begin[nrun] = b; ++nrun; }
+    }
+    run_begin[nrun] = nblk;
+    /* short runs that are too small become general, then equal neighbours merge */
+    for (int i = 0; i < nrun; ++i) {
+        const long long e = run_begin[i + 1] < nblk ? bptr[run_begin[i + 1]] : nz1;
+        if (run_class[i] == 1 && e - bptr[run_begin[i]] < min_nnz) run_class[i] = 0;
+    }
+    int w = 0;
+    for (int i = 0; i < nrun; ++i) {
+        if (w > 0 && run_class[w - 1] == run_class[i]) continue;
+        run_class[w] = run_class[i]; run_begin[w] = run_begin[i]; ++w;
+    }
+    run_begin[w] = nblk;
+    return w;
+}
+
 static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp, const int *col,
                       const int *devices, int src_flags)
 {
     int rc = 0;
     long long *stage64 = NULL;
+    int *d_stats = NULL, *h_stats = NULL, stats_cap = 0;      /* row-block statistics scratch */
     const int dry = (src_flags & SBLAS_LAYOUT_ONLY) != 0;     /* host layout only: no CUDA call at all */
     P->dry = dry;
     if (build_global(P, rp) != 0) { sblas_set_error("%s%s (line %d)", "partition failed", "", __LINE__); return -1; }
@@ -336,9 +382,12 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
         CU(cudaMemsetAsync(D->d_edge, 0, (size_t)(2 * (P->rank_mode ? P->max_local : nl) + 2) * sizeof(double), st));
         }   /* !dry */
 
-        /* ---- segments: kernel choice, tiles */
+        /* ---- segments: kernel choice, panels, tiles */
         pick_kernel(P->kernel, D->nnz, &D->kind, &D->ipt);
-        const int TILE = sblas_tile_size_kind(D->kind, D->ipt);
+        const int panels_on = !dry && P->kernel == 1 && D->kind == SBLAS_K_TMA && !getenv("SBLAS_KIND") &&
+                              env_int("SBLAS_PANELS", 1) != 0;
+        const int short_max = env_int("SBLAS_SHORT_MAX", 4);
+        const long long panel_min_nnz = env_int("SBLAS_PANEL_MIN_NNZ", 1 << 20);
         long long tiles_total = 0;
         for (int s = D->seg_begin; s < D->seg_end; ++s) {
             sblas_seg *S = &P->segs[s];
@@ -352,36 +401,101 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
             if (a->nz1 < a->nz0) a->nz1 = a->nz0;
             a->skip_first = P->g_sf[S->gidx] ? a->row_lo : -1;
             a->skip_last = P->g_sl[S->gidx] ? a->row_hi : -1;
-            a->tile0 = a->nz0 / TILE;
-            a->ntile = (a->nz1 > a->nz0) ? (int)(((long long)a->nz1 - 1) / TILE - a->tile0 + 1) : 0;
             a->nz_total = D->nnz;
             a->mode = env_int("SBLAS_TMA_MODE", 0);
-            S->tile_off = tiles_total;
-            tiles_total += a->ntile + 1;
+            if (!dry) {
+                a->val = D->d_val; a->col = D->d_col; a->rowptr = D->d_rowptr;
+                a->x = D->d_x; a->y = D->d_y;
+                a->edge = D->d_edge + 2 * S->lidx;
+            }
             S->stream = S->lidx % D->nstreams;
+            S->unit_begin = P->nunits;
+
+            /* panels: runs of row blocks of one class */
+            const int nrows = a->row_hi - a->row_lo + 1;
+            const int nblk = (nrows + SBLAS_PANEL_ROWS - 1) / SBLAS_PANEL_ROWS;
+            int nrun = 1;
+            int run_class[SBLAS_PANEL_MAX + 2] = {0}, run_begin[SBLAS_PANEL_MAX + 2] = {0};
+            const int *bptr = NULL;
+            if (panels_on && nblk >= 2 && (long long)a->nz1 - a->nz0 >= 2 * panel_min_nnz) {
+                if (nblk > stats_cap) {
+                    if (d_stats) cudaFree(d_stats);
+                    free(h_stats);
+                    d_stats = NULL; h_stats = NULL;
+                    stats_cap = nblk;
+                    CU(cudaMalloc((void **)&d_stats, (size_t)2 * stats_cap * sizeof(int)));
+                    h_stats = (int *)malloc((size_t)2 * stats_cap * sizeof(int));
+                    if (!h_stats) { rc = 1; goto fail; }
+                }
+                cudaStream_t st0 = D->streams[0];
+                CU(sblas_launch_row_block_stats(D->d_rowptr, a->row_lo, nrows, SBLAS_PANEL_ROWS, a->nz0, a->nz1,
+                                                d_stats, d_stats + nblk, st0));
+                CU(cudaMemcpyAsync(h_stats, d_stats, (size_t)2 * nblk * sizeof(int), cudaMemcpyDeviceToHost, st0));
+                CU(cudaStreamSynchronize(st0));
+                bptr = h_stats + nblk;
+                int *rc_all = (int *)malloc((size_t)(nblk + 2) * sizeof(int));
+                int *rb_all = (int *)malloc((size_t)(nblk + 2) * sizeof(int));
+                if (!rc_all || !rb_all) { free(rc_all); free(rb_all); rc = 1; goto fail; }
+                const int nr = bin_blocks(h_stats, bptr, nblk, a->nz1, short_max, panel_min_nnz, rc_all, rb_all);
+                if (nr >= 2 && nr <= SBLAS_PANEL_MAX) {
+                    nrun = nr;
+                    memcpy(run_class, rc_all, (size_t)nr * sizeof(int));
+                    memcpy(run_begin, rb_all, (size_t)(nr + 1) * sizeof(int));
+                } else if (nr == 1 && rc_all[0] == 1) {
+                    run_class[0] = 1;
+                }
+                free(rc_all); free(rb_all);
+            }
+            if (nrun == 1) { run_begin[0] = 0; run_begin[1] = nblk; }
+            for (int i = 0; i < nrun; ++i) {
+                sblas_unit *U = new_unit(P);
+                if (!U) { rc = 1; goto fail; }
+                U->args = *a;
+                U->kind = run_class[i] ? SBLAS_K_SHORT : D->kind;
+                U->ipt = D->ipt;
+                if (nrun > 1) {
+                    sblas_seg_args *u = &U->args;
+                    u->row_lo = a->row_lo + run_begin[i] * SBLAS_PANEL_ROWS;
+                    u->row_hi = i + 1 < nrun ? a->row_lo + run_begin[i + 1] * SBLAS_PANEL_ROWS - 1 : a->row_hi;
+                    if (i > 0) { u->nz0 = bptr[run_begin[i]]; u->skip_first = -1; }
+                    if (i + 1 < nrun) { u->nz1 = bptr[run_begin[i + 1]]; u->skip_last = -1; }
+                }
+                sblas_seg_args *u = &U->args;
+                const int tiled = (U->kind == SBLAS_K_TMA || U->kind == SBLAS_K_TILE);
+                const int TILE = tiled ? sblas_tile_size_kind(U->kind, U->ipt) : 1;
+                u->tile0 = tiled ? u->nz0 / TILE : 0;
+                u->ntile = (tiled && u->nz1 > u->nz0) ? (int)(((long long)u->nz1 - 1) / TILE - u->tile0 + 1) : 0;
+                U->tile_off = tiles_total;
+                if (tiled) tiles_total += u->ntile + 1;
+            }
+            S->unit_end = P->nunits;
+            S->args.tile0 = P->units[S->unit_begin].args.tile0;          /* informational */
+            S->args.ntile = P->units[S->unit_begin].args.ntile;
         }
+        if (d_stats) cudaFree(d_stats);
+        free(h_stats);
+        d_stats = NULL; h_stats = NULL; stats_cap = 0;
         if (dry) continue;
         cudaStream_t st = D->streams[0];
-        if (D->kind != SBLAS_K_VECTOR && D->kind != SBLAS_K_VECP) {
+        if (tiles_total > 0) {
             CU(cudaMalloc((void **)&D->d_tmeta, (size_t)(tiles_total + 1) * 8 * sizeof(int)));
             CU(cudaMalloc((void **)&D->d_tstart, (size_t)(tiles_total + 1) * sizeof(int)));
             CU(cudaMalloc((void **)&D->d_carry, (size_t)(tiles_total + 1) * sizeof(double)));
             CU(cudaMalloc((void **)&D->d_tail, (size_t)(tiles_total + 1) * sizeof(double)));
         }
         for (int s = D->seg_begin; s < D->seg_end; ++s) {
-            sblas_seg *S = &P->segs[s];
-            sblas_seg_args *a = &S->args;
-            a->val = D->d_val; a->col = D->d_col; a->rowptr = D->d_rowptr;
-            a->x = D->d_x; a->y = D->d_y;
-            a->edge = D->d_edge + 2 * S->lidx;
-            if (D->kind != SBLAS_K_VECTOR && D->kind != SBLAS_K_VECP) {
-                a->tstart = D->d_tstart + S->tile_off;
-                a->tmeta = D->d_tmeta + 8 * S->tile_off;
-                a->carry = D->d_carry + S->tile_off;
-                a->tail = D->d_tail + S->tile_off;
-                if (a->ntile > 0) {
-                    CU(sblas_launch_tile_rows(a, TILE, D->d_tstart + S->tile_off, st));
-                    CU(sblas_launch_tile_meta(a, TILE, D->d_tmeta + 8 * S->tile_off, st));
+            for (int ui = P->segs[s].unit_begin; ui < P->segs[s].unit_end; ++ui) {
+                sblas_unit *U = &P->units[ui];
+                sblas_seg_args *u = &U->args;
+                if (U->kind != SBLAS_K_TMA && U->kind != SBLAS_K_TILE) continue;
+                const int TILE = sblas_tile_size_kind(U->kind, U->ipt);
+                u->tstart = D->d_tstart + U->tile_off;
+                u->tmeta = D->d_tmeta + 8 * U->tile_off;
+                u->carry = D->d_carry + U->tile_off;
+                u->tail = D->d_tail + U->tile_off;
+                if (u->ntile > 0) {
+                    CU(sblas_launch_tile_rows(u, TILE, D->d_tstart + U->tile_off, st));
+                    CU(sblas_launch_tile_meta(u, TILE, D->d_tmeta + 8 * U->tile_off, st));
                 }
             }
         }
@@ -474,6 +588,8 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
     return 0;
 fail:
     if (stage64) cudaFree(stage64);
+    if (d_stats) cudaFree(d_stats);
+    free(h_stats);
     return rc;
 }
 
@@ -566,7 +682,12 @@ static int enqueue_segments(sblas_spmv_plan *P, int d, double alpha, double beta
         if (P->peer_bound)       /* edges go straight into this product's half of the exchange table */
             S->args.edge = P->my_base + (long long)((P->epoch + 1) & 1ull) * P->table_words +
                            (long long)P->rank * (2 * P->max_local) + 2 * S->lidx;
-        CU(sblas_launch_spmv_segment(&S->args, D->kind, D->ipt, 0, D->streams[S->stream]));
+        for (int ui = S->unit_begin; ui < S->unit_end; ++ui) {
+            sblas_unit *U = &P->units[ui];
+            U->args.alpha = alpha; U->args.beta = beta;
+            U->args.edge = S->args.edge;
+            CU(sblas_launch_spmv_segment(&U->args, U->kind, U->ipt, 0, D->streams[S->stream]));
+        }
     }
     for (int c = 1; c < D->nstreams; ++c) {
         CU(cudaEventRecord(D->ev_seg[c], D->streams[c]));
@@ -909,11 +1030,10 @@ double sblas_spmv_plan_alg_bytes(const sblas_spmv_plan *P, int beta_nonzero, lon
 int sblas_spmv_plan_launches(const sblas_spmv_plan *P)
 {
     int n = 0;
-    for (int s = 0; s < P->nseg; ++s) {
-        const sblas_dev *D = &P->devs[P->segs[s].dev];
-        const sblas_seg_args *a = &P->segs[s].args;
-        if (a->row_hi < a->row_lo) continue;
-        n += (D->kind != SBLAS_K_VECTOR && D->kind != SBLAS_K_VECP && a->ntile > 0) ? 2 : 1;
+    for (int ui = 0; ui < P->nunits; ++ui) {
+        const sblas_unit *U = &P->units[ui];
+        if (U->args.row_hi < U->args.row_lo) continue;
+        n += ((U->kind == SBLAS_K_TMA || U->kind == SBLAS_K_TILE) && U->args.ntile > 0) ? 2 : 1;
     }
     for (int d = 0; d < P->ndev; ++d) if (P->devs[d].nmerge > 0) ++n;
     return n;

@@ -256,7 +256,9 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
     /* path W settles the chunk borders of a tile one tile later (no block barrier): what lane 4k of
      * a warp (the row that left its chunk) and warp 0 (the row left open by the previous tile) need */
     bool pend = false;
+#if SBLAS_W_DEFER
     unsigned wpar = 0;       /* phase parity per border mbarrier */
+#endif
     int p_info = 0, p_j = 0, p_row = 0;          /* info = ring | parity << 3 | ext << 4 | k << 5 */
     double p_mine = 0.0, p_yv = 0.0;
     auto settle = [&](bool wait) {

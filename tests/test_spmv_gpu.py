@@ -127,6 +127,29 @@ def test_tma_kernel_reduction_paths(mode, monkeypatch):
         run_all_versions(rp, col, val, x, 2.0, 0.0, y0, (1,), kernels=(1,), what="%s/mode %d beta=0" % (name, mode))
 
 
+@pytest.mark.parametrize("short_max", [2, 4, 8])
+def test_row_panels_pick_a_kernel_per_panel(short_max, monkeypatch):
+    """Adaptive row binning at plan level (kernel = 1): 4096-row blocks whose rows all hold <= short_max
+    entries go to the thread-per-row kernel, the rest to the TMA kernel; panels are cut at row
+    borders inside v1 shards and v2 tasks (split first/last rows stay with the outer panels)."""
+    monkeypatch.setenv("SBLAS_SHORT_MAX", str(short_max))
+    monkeypatch.setenv("SBLAS_PANEL_MIN_NNZ", "2048")
+    monkeypatch.setenv("SBLAS_VEC_BELOW", "1")
+    rng = np.random.default_rng(200 + short_max)
+    lens = np.concatenate([np.full(10000, 2, np.int64), np.full(5000, 150, np.int64), rng.integers(0, 5, size=9000),
+                           np.full(100, 300, np.int64), np.full(5000, 2, np.int64), rng.integers(1, 9, size=6000),
+                           [40000], np.full(9000, 1, np.int64)])
+    m, n = len(lens), 8191
+    rp, col, val = make_csr(rng, m, n, lens)
+    x, y0 = rng.standard_normal(n), rng.standard_normal(m)
+    run_all_versions(rp, col, val, x, -1.75, 0.625, y0, gpu_counts(), kernels=(1,), what="panels short_max=%d" % short_max)
+    run_all_versions(rp, col, val, x, 2.0, 0.0, y0, (1,), kernels=(1,), what="panels beta=0")
+    # the plan really is cut into several launches
+    p = sb.Plan.create_rank(sb.V1, m, n, int(rp[-1]), val, rp, col, 1, 0, 0, kernel=1)
+    assert p.launches >= 5, p.launches
+    p.destroy()
+
+
 def test_row_spanning_many_segments():
     """A row longer than nnz/ngpu (v1) and than nb (v2): >= 3 segments share it."""
     rng = np.random.default_rng(17)
