@@ -309,7 +309,9 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
         const uint32_t eb = empty0 + 8u * s;
         const int nseg = nown + 1;                 /* segment 0 = the row left open by the previous tile */
 
+#if SBLAS_W_DEFER
         if (pend && !((m.w & 6) == 4 && (a.mode & 1) == 0)) settle(true);   /* W tiles settle after their gather */
+#endif
 
         if (nown <= 1) {
             /* ---- A: at most one row starts here: block reduction straight from registers */
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
             /* lane l < k: chunk-local start of row rs+qa+l; other lanes: the chunk end */
             int v = kChunk;
             if (lane < k) {
-                const int r = S.rp_ok ? S.rp[S.rp_off + qa + lane] : __ldg(a.rowptr + rs + qa + lane);
+                const int r = S.rp[S.rp_off + qa + lane];         /* always staged: 2 <= nown <= 56 rows */
                 v = min(max(r, base + clo), base + chi) - base - c0;
             }
 #if SBLAS_W_SHUFFLE
@@ -417,12 +419,17 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
                 mbar_wait(full0 + 8u * sn, phn);
                 gather(st[sn], base + step);
             }
-            if (pend) settle(true);                                  /* the previous tile's chunk borders */
+#if SBLAS_W_DEFER
+            if (pend) settle(true);                              /* the previous tile's chunk borders */
+#endif
             double acc = 0.0, mine = 0.0;
             int cur = 0;
             int nb = __shfl_sync(kFull, v, 0);                   /* next row start (chunk-local), 256 = none */
+            /* bit i: a row starts inside slice i (one warp-wide OR, the result is warp-uniform) */
+            const unsigned hasb = __reduce_or_sync(kFull, lane < k ? 1u << (v >> 5) : 0u);
 #pragma unroll
             for (int i = 0; i < kIPT; ++i) {
+                if ((hasb & (1u << i)) == 0) { acc += p[i]; continue; }
                 int lo_lane = 0;
                 while (nb < 32 * (i + 1)) {                      /* a row starts inside slice i */
                     const int o = nb - 32 * i;
@@ -672,7 +679,9 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
         release_stage(eb, lane);
         s = sn; ph = phn; ++it;
     }
-    if (pend) settle(true);                        /* the last tile's chunk borders */
+#if SBLAS_W_DEFER
+    if (pend) settle(true);                    /* the last tile's chunk borders */
+#endif
 }
 
 int g_sm_count[64] = {0};
