@@ -229,29 +229,47 @@ static sblas_unit *new_unit(sblas_spmv_plan *P)
 #define SBLAS_PANEL_MAX 32             /* most panels per segment (else: one panel) */
 
 /* Adaptive row binning at plan level: cut a segment into panels of consecutive rows by the
- * longest row of every 4096-row block (computed on the GPU): blocks whose rows all hold at most
- * `short_max` entries go to the thread-per-row kernel, everything else to the GPU's general
- * kernel (whose per-tile reduction adapts further).  Short runs below `min_nnz` entries are not
- * worth a launch of their own and join their neighbours.  run_class/run_begin: outputs
- * (run i covers blocks [run_begin[i], run_begin[i+1])); returns the number of runs. */
-static int bin_blocks(const int *bmax, const int *bptr, int nblk, int nz1, int short_max, long long min_nnz,
-                      int *run_class, int *run_begin)
+ * longest row of every 4096-row block (computed on the GPU):
+ *   class 1 "short"   every row holds at most `short_max` entries -> thread-per-row kernel
+ *   class 2 "medium"  longest row in [32, 256] and the rows fill at least half of a warp's
+ *                     256-entry window -> warp per R = floor(256/longest) whole rows (row-tile kernel)
+ *   class 0 "general" everything else -> the GPU's general kernel (the nnz-balanced TMA tile
+ *                     kernel, whose per-tile reduction adapts further)
+ * Runs below `min_nnz` entries are not worth a launch of their own and turn general; equal
+ * neighbours merge (medium runs keep the smallest R).  run_class/run_R/run_begin: outputs (run i
+ * covers blocks [run_begin[i], run_begin[i+1])); returns the number of runs. */
+static int bin_blocks(const int *bmax, const int *bptr, int nblk, int nrows, int nz1, int short_max, int medium_on,
+                      long long min_nnz, int *run_class, int *run_R, int *run_begin)
 {
     int nrun = 0;
     for (int b = 0; b < nblk; ++b) {
-        const int cls = bmax[b] <= short_max;
-        if (nrun == 0 || run_class[nrun - 1] != cls) { run_class[nrun] = cls; run_begin[nrun] = b; ++nrun; }
+        const long long bn = (b + 1 < nblk ? bptr[b + 1] : nz1) - (long long)bptr[b];
+        const long long br = (b + 1 < nblk) ? SBLAS_PANEL_ROWS : nrows - (long long)b * SBLAS_PANEL_ROWS;
+        int cls = 0, R = 0;
+        if (bmax[b] <= short_max) cls = 1;
+        else if (medium_on && bmax[b] >= 32 && bmax[b] <= 256) {
+            R = 256 / bmax[b];
+            if (R > 8) R = 8;
+            if (bn * R >= 128 * br) cls = 2;
+        }
+        if (nrun > 0 && run_class[nrun - 1] == cls) {
+            if (cls == 2 && R < run_R[nrun - 1]) run_R[nrun - 1] = R;
+            continue;
+        }
+        run_class[nrun] = cls; run_R[nrun] = R; run_begin[nrun] = b; ++nrun;
     }
     run_begin[nrun] = nblk;
-    /* short runs that are too small become general, then equal neighbours merge */
     for (int i = 0; i < nrun; ++i) {
         const long long e = run_begin[i + 1] < nblk ? bptr[run_begin[i + 1]] : nz1;
-        if (run_class[i] == 1 && e - bptr[run_begin[i]] < min_nnz) run_class[i] = 0;
+        if (run_class[i] != 0 && e - bptr[run_begin[i]] < min_nnz) run_class[i] = 0;
     }
     int w = 0;
     for (int i = 0; i < nrun; ++i) {
-        if (w > 0 && run_class[w - 1] == run_class[i]) continue;
-        run_class[w] = run_class[i]; run_begin[w] = run_begin[i]; ++w;
+        if (w > 0 && run_class[w - 1] == run_class[i]) {
+            if (run_class[i] == 2 && run_R[i] < run_R[w - 1]) run_R[w - 1] = run_R[i];
+            continue;
+        }
+        run_class[w] = run_class[i]; run_R[w] = run_R[i]; run_begin[w] = run_begin[i]; ++w;
     }
     run_begin[w] = nblk;
     return w;
@@ -387,6 +405,7 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
         const int panels_on = !dry && P->kernel == 1 && D->kind == SBLAS_K_TMA && !getenv("SBLAS_KIND") &&
                               env_int("SBLAS_PANELS", 1) != 0;
         const int short_max = env_int("SBLAS_SHORT_MAX", 4);
+        const int medium_on = env_int("SBLAS_MEDIUM", 1);
         const long long panel_min_nnz = env_int("SBLAS_PANEL_MIN_NNZ", 1 << 20);
         long long tiles_total = 0;
         for (int s = D->seg_begin; s < D->seg_end; ++s) {
@@ -415,9 +434,9 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
             const int nrows = a->row_hi - a->row_lo + 1;
             const int nblk = (nrows + SBLAS_PANEL_ROWS - 1) / SBLAS_PANEL_ROWS;
             int nrun = 1;
-            int run_class[SBLAS_PANEL_MAX + 2] = {0}, run_begin[SBLAS_PANEL_MAX + 2] = {0};
+            int run_class[SBLAS_PANEL_MAX + 2] = {0}, run_R[SBLAS_PANEL_MAX + 2] = {0}, run_begin[SBLAS_PANEL_MAX + 2] = {0};
             const int *bptr = NULL;
-            if (panels_on && nblk >= 2 && (long long)a->nz1 - a->nz0 >= 2 * panel_min_nnz) {
+            if (panels_on && nblk >= 1 && (long long)a->nz1 - a->nz0 >= 2 * panel_min_nnz) {
                 if (nblk > stats_cap) {
                     if (d_stats) cudaFree(d_stats);
                     free(h_stats);
@@ -434,25 +453,28 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
                 CU(cudaStreamSynchronize(st0));
                 bptr = h_stats + nblk;
                 int *rc_all = (int *)malloc((size_t)(nblk + 2) * sizeof(int));
+                int *rr_all = (int *)malloc((size_t)(nblk + 2) * sizeof(int));
                 int *rb_all = (int *)malloc((size_t)(nblk + 2) * sizeof(int));
-                if (!rc_all || !rb_all) { free(rc_all); free(rb_all); rc = 1; goto fail; }
-                const int nr = bin_blocks(h_stats, bptr, nblk, a->nz1, short_max, panel_min_nnz, rc_all, rb_all);
+                if (!rc_all || !rr_all || !rb_all) { free(rc_all); free(rr_all); free(rb_all); rc = 1; goto fail; }
+                const int nr = bin_blocks(h_stats, bptr, nblk, nrows, a->nz1, short_max, medium_on, panel_min_nnz,
+                                          rc_all, rr_all, rb_all);
                 if (nr >= 2 && nr <= SBLAS_PANEL_MAX) {
                     nrun = nr;
                     memcpy(run_class, rc_all, (size_t)nr * sizeof(int));
+                    memcpy(run_R, rr_all, (size_t)nr * sizeof(int));
                     memcpy(run_begin, rb_all, (size_t)(nr + 1) * sizeof(int));
-                } else if (nr == 1 && rc_all[0] == 1) {
-                    run_class[0] = 1;
+                } else if (nr == 1) {
+                    run_class[0] = rc_all[0]; run_R[0] = rr_all[0];
                 }
-                free(rc_all); free(rb_all);
+                free(rc_all); free(rr_all); free(rb_all);
             }
             if (nrun == 1) { run_begin[0] = 0; run_begin[1] = nblk; }
             for (int i = 0; i < nrun; ++i) {
                 sblas_unit *U = new_unit(P);
                 if (!U) { rc = 1; goto fail; }
                 U->args = *a;
-                U->kind = run_class[i] ? SBLAS_K_SHORT : D->kind;
-                U->ipt = D->ipt;
+                U->kind = run_class[i] == 1 ? SBLAS_K_SHORT : run_class[i] == 2 ? SBLAS_K_ROWTILE : D->kind;
+                U->ipt = run_class[i] == 2 ? run_R[i] : D->ipt;
                 if (nrun > 1) {
                     sblas_seg_args *u = &U->args;
                     u->row_lo = a->row_lo + run_begin[i] * SBLAS_PANEL_ROWS;

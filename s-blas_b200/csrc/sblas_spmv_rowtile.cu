@@ -1,0 +1,271 @@
+/* sblas_spmv_rowtile.cu -- SpMV for panels of MEDIUM rows (every row of the panel holds at most
+ * 256 entries, most of them at least 32): warp per R whole rows, TMA-fed.
+ *
+ * Replaces cusparseDcsrmv / cusparseDcsrmv_mp (spmv/src/dspmv_mgpu_v1.cu:200,206,
+ * dspmv_mgpu_v2.cu:351,357, dspmv_mgpu_baseline.cu:163) for the row panels the plan bins as
+ * "medium" (sblas_plan.c); the north star's "warp-per-row" bin.
+ *
+ * The nnz-balanced tile kernel (sblas_spmv_tma.cu) pays for rows that cross chunk and tile
+ * borders: flags or piece bookkeeping, a block barrier per tile, a fix-up pass.  When every row
+ * fits a warp's 256-entry window none of that is needed: a tile is 8*R consecutive WHOLE rows
+ * (R = floor(256 / longest row of the panel), 1..8), warp w owns rows [w*R, (w+1)*R) of it, and
+ * a row never leaves its warp.
+ *
+ *   - grid = 2 CTAs per SM, persistent; tile j goes to CTA j mod grid
+ *   - one producer warp: a single lane issues 1-D bulk copies (cp.async.bulk, SASS UBLKCP) of the
+ *     tile's val and col range (from the 16-byte-aligned entry at or before its first entry) and
+ *     of its 8R+1 row pointers into a 3-stage shared-memory ring; completion on mbarriers, L2
+ *     evict-first; the tile's entry range is looked up one round ahead
+ *   - eight consumer warps; slot i of lane l = entry 32*i + l of the warp's rows (stride-1 across
+ *     lanes: neighbouring columns coalesce in the x gather).  Per tile and warp:
+ *       (1) products of the current tile: val (shared memory) times the x values gathered one
+ *           tile earlier; the stage goes back to the producer
+ *       (2) col reads + x gathers of the NEXT tile into the same registers
+ *       (3) R == 1: tree + one warp reduction, lane 0 writes the row
+ *           R  > 1: lanes add to the running row and park their partial sum where the next row
+ *                   starts; one transposed pass finishes all rows (lanes 4c..4c+3 sum row c)
+ *   - no block barrier, no carry between tiles, no fix-up kernel: every row is written exactly
+ *     once by the warp that owns it (deterministic, no atomics).
+ */
+#include <cuda_runtime.h>
+#include "sblas_dev_common.cuh"
+
+namespace {
+
+using namespace sblas;
+
+constexpr int kWin = 256;                      /* entries a warp handles per tile */
+constexpr int kRtWarps = 8;                    /* consumer warps */
+constexpr int kRtThreads = kRtWarps * 32 + 32; /* + one producer warp */
+constexpr int kRtCap = kRtWarps * kWin + 8;    /* entries staged per tile (+ alignment slack) */
+constexpr int kRtRp = 80;                      /* row pointers staged per tile: 8*8+1, + alignment slack */
+constexpr int kRtStages = 3;
+constexpr int kSlots = kWin / 32;
+
+struct __align__(128) RtStage {
+    double val[kRtCap];
+    int col[kRtCap];
+    int rp[kRtRp];
+    int s0;          /* GPU-local index of val[0] / col[0] */
+    int rp_off;      /* rp[rp_off + q] == rowptr[first row of the tile + q] */
+    int nrows;       /* rows of the tile (8R except in the last tile) */
+    int pad;
+};
+
+constexpr int kRtBarBytes = 2 * kRtStages * 8;
+constexpr int kRtScratch = 8 * 32;             /* doubles per warp: P[row][lane] */
+constexpr int kRtSmem = kRtStages * (int)sizeof(RtStage) + kRtBarBytes + kRtWarps * kRtScratch * 8;
+
+__global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas_seg_args a, const int R)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    RtStage *st = reinterpret_cast<RtStage *>(smem);
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t full0 = smem0 + (uint32_t)(kRtStages * sizeof(RtStage));
+    const uint32_t empty0 = full0 + 8u * kRtStages;
+    double *scratch = reinterpret_cast<double *>(smem + kRtStages * sizeof(RtStage) + kRtBarBytes);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ncta = gridDim.x, cta = blockIdx.x;
+    const int rows_per_tile = kRtWarps * R;
+    const int nrows_all = a.row_hi - a.row_lo + 1;
+    const int ntile = (nrows_all + rows_per_tile - 1) / rows_per_tile;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kRtStages; ++s) {
+            mbar_init(full0 + 8u * s, 1);
+            mbar_init(empty0 + 8u * s, kRtWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == kRtWarps) {
+        /* ------------------------------------------------------------ producer */
+        if (lane == 0) {
+            const uint64_t pol = policy_evict_first();
+            int j = cta;
+            /* entry range of tile j: [rowptr[r0], rowptr[r1]) clamped to the segment */
+            auto bounds = [&](int jj, int &r0, int &r1, int &e0, int &e1) {
+                r0 = a.row_lo + jj * rows_per_tile;
+                r1 = min(r0 + rows_per_tile, a.row_hi + 1);
+                e0 = __ldg(a.rowptr + r0);
+                e1 = __ldg(a.rowptr + r1);
+            };
+            int r0n = 0, r1n = 0, e0n = 0, e1n = 0;
+            if (j < ntile) bounds(j, r0n, r1n, e0n, e1n);
+            int s = 0;
+            uint32_t ph = 0;
+            for (; j < ntile; j += ncta) {
+                const int r0 = r0n, r1 = r1n;
+                const int e0 = min(max(e0n, a.nz0), a.nz1), e1 = min(max(e1n, a.nz0), a.nz1);
+                if (j + ncta < ntile) bounds(j + ncta, r0n, r1n, e0n, e1n);
+                mbar_wait(empty0 + 8u * s, ph ^ 1u);
+                const int s0 = e0 & ~3;                                  /* 32-byte aligned in val, 16 in col */
+                const int cnt = min(e1, a.nz_total) - s0;                /* <= 2048 + 3 */
+                const uint32_t vb = cnt > 0 ? (((uint32_t)cnt * 8u + 15u) & ~15u) : 0u;
+                const uint32_t cb = cnt > 0 ? (((uint32_t)cnt * 4u + 15u) & ~15u) : 0u;
+                const int rp0 = r0 & ~3;
+                const uint32_t rb = (uint32_t)(((r1 - rp0 + 1) + 3) & ~3) * 4u;
+                st[s].s0 = s0;
+                st[s].rp_off = r0 - rp0;
+                st[s].nrows = r1 - r0;
+                const uint32_t sbase = smem0 + (uint32_t)(s * sizeof(RtStage));
+                const uint32_t fb = full0 + 8u * s;
+                mbar_arrive_expect_tx(fb, vb + cb + rb);
+                if (cnt > 0) {
+                    bulk_g2s(sbase, a.val + s0, vb, fb, pol);
+                    bulk_g2s(sbase + kRtCap * 8, a.col + s0, cb, fb, pol);
+                }
+                bulk_g2s(sbase + kRtCap * 12, a.rowptr + rp0, rb, fb, pol);
+                if (++s == kRtStages) { s = 0; ph ^= 1u; }
+            }
+        }
+        return;
+    }
+
+    /* ---------------------------------------------------------------- consumers */
+    int j = cta;
+    if (j >= ntile) return;
+    const double *__restrict__ xp = a.x;
+    const bool has_y = a.beta != 0.0;
+    double *P = scratch + warp * kRtScratch;
+
+    /* state of the tile whose x values sit in xv */
+    double xv[kSlots];
+    int cb = 0, ce = 0;       /* my rows' entries, stage-local [cb, ce) */
+    int first = 0, nr = 0;    /* my rows: first (GPU-local row id) and how many */
+    int v = kWin;             /* lane q < nr-1: where row first+q+1 starts, relative to cb; else kWin */
+
+    auto gather = [&](const RtStage &S, int jj) {
+        const int r0 = a.row_lo + jj * rows_per_tile;
+        const int mine0 = min(warp * R, S.nrows);
+        nr = min(R, S.nrows - mine0);
+        first = r0 + mine0;
+        const int *rp = S.rp + S.rp_off + mine0;
+        /* lane q <= nr reads the q-th boundary of my rows */
+        int b = 0;
+        if (lane <= nr) b = min(max(rp[lane], a.nz0), a.nz1) - S.s0;
+        cb = __shfl_sync(kFull, b, 0);
+        ce = __shfl_sync(kFull, b, nr);
+        const int nxt = __shfl_down_sync(kFull, b, 1);
+        v = (lane + 1 < nr) ? nxt - cb : kWin;
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) {
+            const int pos = cb + 32 * i + lane;
+            xv[i] = 0.0;
+            if (pos < ce) xv[i] = __ldg(xp + (unsigned)S.col[pos]);
+        }
+    };
+
+    int s = 0;
+    uint32_t ph = 0;
+    mbar_wait(full0, 0u);
+    gather(st[0], j);
+
+    for (; j < ntile; j += ncta) {
+        RtStage &S = st[s];
+        int sn = s + 1;
+        uint32_t phn = ph;
+        if (sn == kRtStages) { sn = 0; phn ^= 1u; }
+        const bool has_next = j + ncta < ntile;
+        const int ccb = cb, cce = ce, cfirst = first, cnr = nr, cv = v;
+
+        /* (1) products; slots past the end of my rows are zero */
+        double p[kSlots];
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) {
+            const int pos = ccb + 32 * i + lane;
+            p[i] = (pos < cce) ? S.val[pos] * xv[i] : 0.0;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8u * s);
+
+        /* y of the rows I will write: lane 4c owns row cfirst + c (R == 1: lane 0) */
+        const int pc = lane >> 2;
+        const int myrow = cfirst + pc;
+        const bool owner = (lane & 3) == 0 && pc < cnr;
+        double yv = 0.0;
+        if (has_y && owner && myrow != a.skip_first && myrow != a.skip_last) yv = a.y[myrow];
+
+        /* (2) the next tile's gathers go out before the sums */
+        if (has_next) {
+            mbar_wait(full0 + 8u * sn, phn);
+            gather(st[sn], j + ncta);
+        }
+
+        /* (3) row sums */
+        double mine;
+        if (R == 1) {
+            double t = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+            mine = warp_sum(t);
+        } else {
+            double acc = 0.0;
+            int cur = 0;
+            int nb = __shfl_sync(kFull, cv, 0);                  /* next row start relative to ccb, 256 = none */
+            const unsigned hasb = __reduce_or_sync(kFull, (lane + 1 < cnr && cv < kWin) ? 1u << (cv >> 5) : 0u);
+#pragma unroll
+            for (int i = 0; i < kSlots; ++i) {
+                if ((hasb & (1u << i)) == 0) { acc += p[i]; continue; }
+                int lo_lane = 0;
+                while (nb < 32 * (i + 1)) {                      /* a row starts inside slice i */
+                    const int o = nb - 32 * i;
+                    if (lane >= lo_lane && lane < o) acc += p[i];
+                    P[cur * 32 + lane] = acc;
+                    acc = 0.0;
+                    lo_lane = o;
+                    ++cur;
+                    nb = __shfl_sync(kFull, cv, cur);
+                }
+                if (lane >= lo_lane) acc += p[i];
+            }
+            P[cur * 32 + lane] = acc;                            /* my last row with entries */
+            for (++cur; cur < cnr; ++cur) P[cur * 32 + lane] = 0.0;   /* empty rows at the end of my window */
+            __syncwarp();
+            /* lane (c, q) takes elements 16h + 4q + ((c + e) & 3), e = 0..7, h = e >> 2: every load is
+             * bank-conflict-free and the four lanes of a row cover its 32 partial sums */
+            const double *Q = P + pc * 32 + 4 * (lane & 3);
+            double t[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) t[e] = Q[16 * (e >> 2) + ((pc + e) & 3)];
+            mine = ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+            mine += __shfl_xor_sync(kFull, mine, 1);
+            mine += __shfl_xor_sync(kFull, mine, 2);             /* rows beyond cnr: unused garbage */
+            __syncwarp();                                        /* P is rewritten by the next tile */
+        }
+        if (owner) {
+            if (myrow == a.skip_first) a.edge[0] = mine;
+            else if (myrow == a.skip_last) a.edge[1] = mine;
+            else a.y[myrow] = a.alpha * mine + a.beta * yv;
+        }
+        s = sn; ph = phn;
+    }
+}
+
+int g_rt_sm_count[64] = {0};
+
+}  // namespace
+
+/* y[rows] = alpha*A*x + beta*y for a panel whose rows all hold at most 256/R entries */
+cudaError_t sblas_launch_rowtile(const sblas_seg_args *a, int R, cudaStream_t s)
+{
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 64 || R < 1 || R > 8) return cudaErrorInvalidValue;
+    if (!attr_done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(spmv_rowtile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmem);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&g_rt_sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        attr_done[dev] = true;
+    }
+    const int nrows = a->row_hi - a->row_lo + 1;
+    if (nrows <= 0) return cudaSuccess;
+    const int ntile = (nrows + 8 * R - 1) / (8 * R);
+    int grid = 2 * g_rt_sm_count[dev];
+    if (grid > ntile) grid = ntile;
+    spmv_rowtile_kernel<<<grid, kRtThreads, kRtSmem, s>>>(*a, R);
+    return cudaGetLastError();
+}

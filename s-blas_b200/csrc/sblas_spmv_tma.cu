@@ -57,7 +57,11 @@ constexpr int kGroups = 1;                     /* consumer groups per CTA, each 
 constexpr int kCtasPerSm = SBLAS_TMA_CTAS;
 constexpr int kThreadsTma = kGroups * kConsumers + 32;   /* + one producer warp */
 constexpr int kIPT = kTile / kConsumers;       /* 8 products per consumer thread */
-constexpr int kRpCap = 1032;                   /* row-pointer ints staged per tile (x4) */
+#ifndef SBLAS_W_SCRATCH
+#define SBLAS_W_SCRATCH 0
+#endif
+constexpr int kRpCap = SBLAS_W_SCRATCH ? 264 : 1032;   /* row-pointer ints staged per tile (x4) */
+constexpr int kScratchDoubles = SBLAS_W_SCRATCH ? 256 : 0;    /* path W scratch per consumer warp */
 constexpr int kStages = SBLAS_TMA_STAGES;
 constexpr int kChunk = kTile / kCWarps;             /* entries owned by one consumer warp */
 
@@ -77,7 +81,7 @@ constexpr int kRing = 8;                       /* partial-sum buffers / named-ba
 static_assert(kGroups * kRing < 16, "named barrier ids");
 constexpr int kRedDoubles = kRing * (2 + 3) * kCWarps;          /* per group */
 constexpr int kBarBytes = (2 * kStages + kGroups * kRing) * 8;  /* full[], empty[], border[] mbarriers */
-constexpr int kSmemBytes = kStages * (int)sizeof(Stage) + kBarBytes + kGroups * kRedDoubles * 8;
+constexpr int kSmemBytes = kStages * (int)sizeof(Stage) + kBarBytes + kGroups * (kRedDoubles + kCWarps * kScratchDoubles) * 8;
 
 __device__ __forceinline__ void release_stage(uint32_t empty_bar, int lane)
 {
@@ -406,6 +410,10 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
             }
 #if SBLAS_W_SHUFFLE
             release_stage(eb, lane);                             /* the stage is not touched again */
+#elif SBLAS_W_SCRATCH
+            release_stage(eb, lane);                             /* the stage is not touched again */
+            double *pieces = reinterpret_cast<double *>(smem + kStages * sizeof(Stage) + kBarBytes) +
+                             kGroups * kRedDoubles + (grp * kCWarps + warp) * kScratchDoubles;
 #else
             double *pieces = S.val + c0;                         /* scratch: my own (consumed) slice of val */
 #endif
@@ -462,8 +470,10 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
                 mine += __shfl_xor_sync(kFull, mine, 1);
                 mine += __shfl_xor_sync(kFull, mine, 2);         /* pieces beyond k: unused garbage */
             }
+#if !SBLAS_W_SCRATCH
             fence_proxy_async_smem();          /* generic writes to the slot before the next bulk copy */
             release_stage(eb, lane);
+#endif
 #endif
             if (owner && pc < k) {             /* rows that start and end inside my chunk */
                 if (myrow == a.skip_first) a.edge[0] = mine;

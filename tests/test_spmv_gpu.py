@@ -150,6 +150,32 @@ def test_row_panels_pick_a_kernel_per_panel(short_max, monkeypatch):
     p.destroy()
 
 
+def test_row_tile_kernel_on_medium_panels(monkeypatch):
+    """Panels of medium rows (longest row of a 4096-row block in [32, 256]) go to the row-tile kernel,
+    warp per R = floor(256/longest) whole rows.  One block per R = 1..8, with empty and very short
+    rows sprinkled in, unsorted columns, split rows at shard/task borders (v1 x ngpu, v2 tasks)."""
+    monkeypatch.setenv("SBLAS_PANEL_MIN_NNZ", "2048")
+    monkeypatch.setenv("SBLAS_VEC_BELOW", "1")
+    rng = np.random.default_rng(77)
+    blocks = []
+    for longest in (256, 128, 85, 64, 51, 42, 36, 32, 200, 100):
+        ln = rng.integers(longest // 2 + 1, longest + 1, size=4096)
+        ln[rng.integers(0, 4096, size=40)] = 0
+        ln[rng.integers(0, 4096, size=40)] = rng.integers(1, 4, size=40)
+        ln[rng.integers(0, 4096)] = longest
+        blocks.append(ln)
+    blocks.insert(3, np.full(5000, 2, np.int64))            # a short panel in between
+    blocks.append(np.array([3000, 1, 0, 700], np.int64))    # and a general tail
+    lens = np.concatenate(blocks).astype(np.int64)
+    m, n = len(lens), 16381
+    rp, col, val = make_csr(rng, m, n, lens, sort_cols=False)
+    x, y0 = rng.standard_normal(n), rng.standard_normal(m)
+    run_all_versions(rp, col, val, x, -1.75, 0.625, y0, gpu_counts(), kernels=(1,), what="row tiles")
+    run_all_versions(rp, col, val, x, 2.0, 0.0, y0, (1,), kernels=(1,), what="row tiles beta=0")
+    monkeypatch.setenv("SBLAS_MEDIUM", "0")
+    run_all_versions(rp, col, val, x, -1.75, 0.625, y0, (1,), kernels=(1,), what="row tiles off")
+
+
 def test_row_spanning_many_segments():
     """A row longer than nnz/ngpu (v1) and than nb (v2): >= 3 segments share it."""
     rng = np.random.default_rng(17)
