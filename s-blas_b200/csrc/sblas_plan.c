@@ -231,13 +231,21 @@ static sblas_unit *new_unit(sblas_spmv_plan *P)
 /* Adaptive row binning at plan level: cut a segment into panels of consecutive rows by the
  * longest row of every 4096-row block (computed on the GPU):
  *   class 1 "short"   every row holds at most `short_max` entries -> thread-per-row kernel
- *   class 2 "medium"  longest row in [32, 256] and the rows fill at least half of a warp's
+ *   class 2 "medium"  longest row in [16, 256] and the rows fill at least half of a warp's
  *                     256-entry window -> warp per R = floor(256/longest) whole rows (row-tile kernel)
  *   class 0 "general" everything else -> the GPU's general kernel (the nnz-balanced TMA tile
  *                     kernel, whose per-tile reduction adapts further)
  * Runs below `min_nnz` entries are not worth a launch of their own and turn general; equal
  * neighbours merge (medium runs keep the smallest R).  run_class/run_R/run_begin: outputs (run i
  * covers blocks [run_begin[i], run_begin[i+1])); returns the number of runs. */
+/* (R | longest << 8) of two medium runs that merge: the smaller R, the longer row */
+static int merge_R(int x, int y)
+{
+    const int R = (x & 0xff) < (y & 0xff) ? (x & 0xff) : (y & 0xff);
+    const int mx = (x >> 8) > (y >> 8) ? (x >> 8) : (y >> 8);
+    return R | mx << 8;
+}
+
 static int bin_blocks(const int *bmax, const int *bptr, int nblk, int nrows, int nz1, int short_max, int medium_on,
                       long long min_nnz, int *run_class, int *run_R, int *run_begin)
 {
@@ -247,13 +255,14 @@ static int bin_blocks(const int *bmax, const int *bptr, int nblk, int nrows, int
         const long long br = (b + 1 < nblk) ? SBLAS_PANEL_ROWS : nrows - (long long)b * SBLAS_PANEL_ROWS;
         int cls = 0, R = 0;
         if (bmax[b] <= short_max) cls = 1;
-        else if (medium_on && bmax[b] >= 32 && bmax[b] <= 256) {
+        else if (medium_on && bmax[b] >= 16 && bmax[b] <= 256) {
             R = 256 / bmax[b];
             if (R > 8) R = 8;
             if (bn * R >= 128 * br) cls = 2;
         }
+        if (cls == 2) R |= bmax[b] << 8;                     /* R | longest row << 8 */
         if (nrun > 0 && run_class[nrun - 1] == cls) {
-            if (cls == 2 && R < run_R[nrun - 1]) run_R[nrun - 1] = R;
+            if (cls == 2) run_R[nrun - 1] = merge_R(run_R[nrun - 1], R);
             continue;
         }
         run_class[nrun] = cls; run_R[nrun] = R; run_begin[nrun] = b; ++nrun;
@@ -266,7 +275,7 @@ static int bin_blocks(const int *bmax, const int *bptr, int nblk, int nrows, int
     int w = 0;
     for (int i = 0; i < nrun; ++i) {
         if (w > 0 && run_class[w - 1] == run_class[i]) {
-            if (run_class[i] == 2 && run_R[i] < run_R[w - 1]) run_R[w - 1] = run_R[i];
+            if (run_class[i] == 2) run_R[w - 1] = merge_R(run_R[w - 1], run_R[i]);
             continue;
         }
         run_class[w] = run_class[i]; run_R[w] = run_R[i]; run_begin[w] = run_begin[i]; ++w;
@@ -474,7 +483,11 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
                 if (!U) { rc = 1; goto fail; }
                 U->args = *a;
                 U->kind = run_class[i] == 1 ? SBLAS_K_SHORT : run_class[i] == 2 ? SBLAS_K_ROWTILE : D->kind;
-                U->ipt = run_class[i] == 2 ? run_R[i] : D->ipt;
+                U->ipt = D->ipt;
+                if (run_class[i] == 2) {           /* R rows per warp, window = R x longest row (<= 256) */
+                    const int R = run_R[i] & 0xff, win = R * (run_R[i] >> 8);
+                    U->ipt = R | (win < 256 ? win : 256) << 8;
+                }
                 if (nrun > 1) {
                     sblas_seg_args *u = &U->args;
                     u->row_lo = a->row_lo + run_begin[i] * SBLAS_PANEL_ROWS;

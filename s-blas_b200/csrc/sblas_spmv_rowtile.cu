@@ -40,7 +40,6 @@ constexpr int kRtThreads = kRtWarps * 32 + 32; /* + one producer warp */
 constexpr int kRtCap = kRtWarps * kWin + 8;    /* entries staged per tile (+ alignment slack) */
 constexpr int kRtRp = 80;                      /* row pointers staged per tile: 8*8+1, + alignment slack */
 constexpr int kRtStages = 3;
-constexpr int kSlots = kWin / 32;
 
 struct __align__(128) RtStage {
     double val[kRtCap];
@@ -56,6 +55,8 @@ constexpr int kRtBarBytes = 2 * kRtStages * 8;
 constexpr int kRtScratch = 8 * 32;             /* doubles per warp: P[row][lane] */
 constexpr int kRtSmem = kRtStages * (int)sizeof(RtStage) + kRtBarBytes + kRtWarps * kRtScratch * 8;
 
+/* NS = slots per lane: the panel's R rows hold at most 32*NS entries */
+template <int NS>
 __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas_seg_args a, const int R)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -133,10 +134,11 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas
     double *P = scratch + warp * kRtScratch;
 
     /* state of the tile whose x values sit in xv */
-    double xv[kSlots];
+    double xv[NS];
     int cb = 0, ce = 0;       /* my rows' entries, stage-local [cb, ce) */
     int first = 0, nr = 0;    /* my rows: first (GPU-local row id) and how many */
     int v = kWin;             /* lane q < nr-1: where row first+q+1 starts, relative to cb; else kWin */
+    double yv = 0.0;          /* lane 4c, c < nr: y of row first+c (loaded a whole tile ahead of its use) */
 
     auto gather = [&](const RtStage &S, int jj) {
         const int r0 = a.row_lo + jj * rows_per_tile;
@@ -151,8 +153,13 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas
         ce = __shfl_sync(kFull, b, nr);
         const int nxt = __shfl_down_sync(kFull, b, 1);
         v = (lane + 1 < nr) ? nxt - cb : kWin;
+        {
+            const int row = first + (lane >> 2);
+            yv = 0.0;
+            if (has_y && (lane & 3) == 0 && (lane >> 2) < nr && row != a.skip_first && row != a.skip_last) yv = a.y[row];
+        }
 #pragma unroll
-        for (int i = 0; i < kSlots; ++i) {
+        for (int i = 0; i < NS; ++i) {
             const int pos = cb + 32 * i + lane;
             xv[i] = 0.0;
             if (pos < ce) xv[i] = __ldg(xp + (unsigned)S.col[pos]);
@@ -171,23 +178,22 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas
         if (sn == kRtStages) { sn = 0; phn ^= 1u; }
         const bool has_next = j + ncta < ntile;
         const int ccb = cb, cce = ce, cfirst = first, cnr = nr, cv = v;
+        const double cyv = yv;
 
         /* (1) products; slots past the end of my rows are zero */
-        double p[kSlots];
+        double p[NS];
 #pragma unroll
-        for (int i = 0; i < kSlots; ++i) {
+        for (int i = 0; i < NS; ++i) {
             const int pos = ccb + 32 * i + lane;
             p[i] = (pos < cce) ? S.val[pos] * xv[i] : 0.0;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8u * s);
 
-        /* y of the rows I will write: lane 4c owns row cfirst + c (R == 1: lane 0) */
+        /* lane 4c owns row cfirst + c (R == 1: lane 0) */
         const int pc = lane >> 2;
         const int myrow = cfirst + pc;
         const bool owner = (lane & 3) == 0 && pc < cnr;
-        double yv = 0.0;
-        if (has_y && owner && myrow != a.skip_first && myrow != a.skip_last) yv = a.y[myrow];
 
         /* (2) the next tile's gathers go out before the sums */
         if (has_next) {
@@ -198,15 +204,19 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas
         /* (3) row sums */
         double mine;
         if (R == 1) {
-            double t = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
-            mine = warp_sum(t);
+            double t = p[0], t1 = p[1];
+#pragma unroll
+            for (int i = 2; i < NS; i += 2) t += p[i];
+#pragma unroll
+            for (int i = 3; i < NS; i += 2) t1 += p[i];
+            mine = warp_sum(t + t1);
         } else {
             double acc = 0.0;
             int cur = 0;
             int nb = __shfl_sync(kFull, cv, 0);                  /* next row start relative to ccb, 256 = none */
             const unsigned hasb = __reduce_or_sync(kFull, (lane + 1 < cnr && cv < kWin) ? 1u << (cv >> 5) : 0u);
 #pragma unroll
-            for (int i = 0; i < kSlots; ++i) {
+            for (int i = 0; i < NS; ++i) {
                 if ((hasb & (1u << i)) == 0) { acc += p[i]; continue; }
                 int lo_lane = 0;
                 while (nb < 32 * (i + 1)) {                      /* a row starts inside slice i */
@@ -237,7 +247,7 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas
         if (owner) {
             if (myrow == a.skip_first) a.edge[0] = mine;
             else if (myrow == a.skip_last) a.edge[1] = mine;
-            else a.y[myrow] = a.alpha * mine + a.beta * yv;
+            else a.y[myrow] = a.alpha * mine + a.beta * cyv;
         }
         s = sn; ph = phn;
     }
@@ -247,15 +257,19 @@ int g_rt_sm_count[64] = {0};
 
 }  // namespace
 
-/* y[rows] = alpha*A*x + beta*y for a panel whose rows all hold at most 256/R entries */
-cudaError_t sblas_launch_rowtile(const sblas_seg_args *a, int R, cudaStream_t s)
+/* y[rows] = alpha*A*x + beta*y for a panel whose rows all hold at most 256/R entries;
+ * window = the most entries R consecutive rows of the panel can hold (<= 256) */
+cudaError_t sblas_launch_rowtile(const sblas_seg_args *a, int R, int window, cudaStream_t s)
 {
     static bool attr_done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 64 || R < 1 || R > 8) return cudaErrorInvalidValue;
     if (!attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(spmv_rowtile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmem);
+        cudaError_t e = cudaSuccess;
+#define RT_ATTR(NS) if (e == cudaSuccess) e = cudaFuncSetAttribute(spmv_rowtile_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmem)
+        RT_ATTR(4); RT_ATTR(5); RT_ATTR(6); RT_ATTR(7); RT_ATTR(8);
+#undef RT_ATTR
         if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&g_rt_sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
@@ -266,6 +280,14 @@ cudaError_t sblas_launch_rowtile(const sblas_seg_args *a, int R, cudaStream_t s)
     const int ntile = (nrows + 8 * R - 1) / (8 * R);
     int grid = 2 * g_rt_sm_count[dev];
     if (grid > ntile) grid = ntile;
-    spmv_rowtile_kernel<<<grid, kRtThreads, kRtSmem, s>>>(*a, R);
+    int ns = (window + 31) / 32;
+    if (window <= 0 || ns > 8) ns = 8;
+    switch (ns) {
+    case 1: case 2: case 3: case 4: spmv_rowtile_kernel<4><<<grid, kRtThreads, kRtSmem, s>>>(*a, R); break;
+    case 5: spmv_rowtile_kernel<5><<<grid, kRtThreads, kRtSmem, s>>>(*a, R); break;
+    case 6: spmv_rowtile_kernel<6><<<grid, kRtThreads, kRtSmem, s>>>(*a, R); break;
+    case 7: spmv_rowtile_kernel<7><<<grid, kRtThreads, kRtSmem, s>>>(*a, R); break;
+    default: spmv_rowtile_kernel<8><<<grid, kRtThreads, kRtSmem, s>>>(*a, R); break;
+    }
     return cudaGetLastError();
 }
