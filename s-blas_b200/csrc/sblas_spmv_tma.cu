@@ -1,9 +1,11 @@
-/* sblas_spmv_tma.cu -- the main SpMV kernel: persistent, warp-specialised, TMA-fed.
+/* sblas_spmv_tma.cu -- the GENERAL SpMV kernel: persistent, warp-specialised, TMA-fed,
+ * nnz-balanced tiles; whatever the rows look like.
  *
  * Replaces cusparseDcsrmv_mp / cusparseDcsrmv (spmv/src/dspmv_mgpu_v1.cu:200,206,
  * dspmv_mgpu_v2.cu:351,357, dspmv_mgpu_baseline.cu:163) and the CSR5 tile kernels
- * (spmv/include/detail/cuda/csr5_spmv_cuda.h:275-311) for everything big enough to
- * fill the GPU.
+ * (spmv/include/detail/cuda/csr5_spmv_cuda.h:275-311).  The plan sends row panels that are
+ * uniformly short or medium to leaner kernels (spmv_short_kernel, sblas_spmv_rowtile.cu);
+ * everything else -- long rows, mixed and power-law rows -- runs here.
  *
  * SpMV is HBM-bound (12 B streamed per nnz, 2 flop): the kernel is built around keeping
  * as many bytes in flight per SM as possible with no register or LSU cost, and around a
@@ -15,17 +17,21 @@
  *     of the tile's val (16 KB), col (8 KB) and -- when the tile holds several rows -- its
  *     slice of the row pointer into a 3-stage shared-memory ring, completion counted on
  *     mbarriers, L2 evict-first so the stream does not push x out of L2; the per-tile
- *     metadata (one int4) is prefetched one round ahead
- *   - eight consumer warps, element i of thread t = tile-local index i*256 + t (stride-1
- *     across lanes, so the x gather of neighbouring columns coalesces).  Per tile:
+ *     metadata (two int4) is prefetched one round ahead
+ *   - eight consumer warps; every warp owns a contiguous 256-entry chunk of the tile, element
+ *     i of lane l = chunk entry 32*i + l (stride-1 across lanes, so the x gather of
+ *     neighbouring columns coalesces).  Per tile:
  *       (1) multiply val (shared memory) by the x values gathered one iteration earlier,
  *       (2) issue the col reads + x gathers of the NEXT tile into the same registers,
- *       (3) reduce the current tile while those gathers are in flight:
- *             <= 1 row starts in the tile (long rows) -> block reduction from registers;
- *                only warp 0 waits on the named barrier, the others bar.arrive and go on
- *             several rows -> products in place over val, then G lanes per row:
- *                G = 32 warp-per-row, 2..16 sub-warp, 1 thread-per-row; beta*y of the rows a
- *                lane will write is loaded before the barrier
+ *       (3) reduce the current tile while those gathers are in flight; the path is picked per
+ *           tile from its metadata (adaptive binning at tile granularity):
+ *             A  <= 1 row starts in the tile (rows >= 2048): FMA into registers, warp shuffle,
+ *                8 partials through shared memory; only warp 0 waits on the named barrier
+ *             W  <= 7 row starts per chunk, none empty (rows ~ 32 .. 2048): the row starts cut
+ *                a chunk into pieces; lanes add to the running piece and park partial sums
+ *                where a row starts, one transposed pass finishes all pieces
+ *             M  several short rows, none empty: byte flags + lane walk + one segmented scan
+ *             S  tiles with empty rows: products in place, G = 1..32 lanes per row
  *   - rows that leave their tile are finished by spmv_tile_fixup in a fixed order
  *     (deterministic; no floating-point atomics).
  */
@@ -42,12 +48,6 @@ constexpr int kCWarps = kConsumers / 32;
 constexpr int kGroups = 1;                     /* consumer groups per CTA, each on its own tile (3 groups on a
                                                   7-stage ring, one CTA per SM, measured slower: every group holds
                                                   two stages, which starves the ring) */
-#ifndef SBLAS_W_SHUFFLE
-#define SBLAS_W_SHUFFLE 0
-#endif
-#ifndef SBLAS_W_DEFER
-#define SBLAS_W_DEFER 0
-#endif
 #ifndef SBLAS_TMA_CTAS
 #define SBLAS_TMA_CTAS 2
 #endif
@@ -57,11 +57,7 @@ constexpr int kGroups = 1;                     /* consumer groups per CTA, each 
 constexpr int kCtasPerSm = SBLAS_TMA_CTAS;
 constexpr int kThreadsTma = kGroups * kConsumers + 32;   /* + one producer warp */
 constexpr int kIPT = kTile / kConsumers;       /* 8 products per consumer thread */
-#ifndef SBLAS_W_SCRATCH
-#define SBLAS_W_SCRATCH 0
-#endif
-constexpr int kRpCap = SBLAS_W_SCRATCH ? 264 : 1032;   /* row-pointer ints staged per tile (x4) */
-constexpr int kScratchDoubles = SBLAS_W_SCRATCH ? 256 : 0;    /* path W scratch per consumer warp */
+constexpr int kRpCap = 1032;                   /* row-pointer ints staged per tile (x4) */
 constexpr int kStages = SBLAS_TMA_STAGES;
 constexpr int kChunk = kTile / kCWarps;             /* entries owned by one consumer warp */
 
@@ -75,13 +71,12 @@ struct __align__(128) Stage {
     int rp_ok;       /* the row pointer slice was staged */
 };
 
-constexpr int kRing = 8;                       /* partial-sum buffers / named-barrier ids / border mbarriers.  A warp
-                                                  is at most kStages tiles ahead of the slowest one and path W
-                                                  settles a tile's chunk borders during the NEXT tile: 8 slots */
+constexpr int kRing = 4;                       /* partial-sum buffers / named-barrier ids: a warp is at most
+                                                  kStages tiles ahead of the slowest one, so 4 slots suffice */
 static_assert(kGroups * kRing < 16, "named barrier ids");
 constexpr int kRedDoubles = kRing * (2 + 3) * kCWarps;          /* per group */
-constexpr int kBarBytes = (2 * kStages + kGroups * kRing) * 8;  /* full[], empty[], border[] mbarriers */
-constexpr int kSmemBytes = kStages * (int)sizeof(Stage) + kBarBytes + kGroups * (kRedDoubles + kCWarps * kScratchDoubles) * 8;
+constexpr int kBarBytes = 2 * kStages * 8;                      /* full[], empty[] mbarriers */
+constexpr int kSmemBytes = kStages * (int)sizeof(Stage) + kBarBytes + kGroups * kRedDoubles * 8;
 
 __device__ __forceinline__ void release_stage(uint32_t empty_bar, int lane)
 {
@@ -163,7 +158,6 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
     const uint32_t empty0 = full0 + 8u * kStages;                           /* empty[s] = empty0 + 8 s */
     const int tid = threadIdx.x, pw = tid >> 5, lane = tid & 31;
     const int grp = pw / kCWarps, warp = pw % kCWarps;      /* consumer group, warp inside the group */
-    const uint32_t wcbar0 = empty0 + 8u * kStages + 8u * kRing * grp;       /* border[r] = wcbar0 + 8 r */
     double *red = reinterpret_cast<double *>(smem + kStages * sizeof(Stage) + kBarBytes) + grp * kRedDoubles;
     const int ncta = gridDim.x, cta = blockIdx.x;
     const int ntile = a.ntile;
@@ -174,7 +168,6 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
             mbar_init(full0 + 8u * s, 1);
             mbar_init(empty0 + 8u * s, kCWarps);
         }
-        for (int r = 0; r < kGroups * kRing; ++r) mbar_init(empty0 + 8u * kStages + 8u * r, kCWarps);
         mbar_fence_init();
     }
     __syncthreads();
@@ -257,19 +250,10 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
         }
     };
 
-    /* path W settles the chunk borders of a tile one tile later (no block barrier): what lane 4k of
-     * a warp (the row that left its chunk) and warp 0 (the row left open by the previous tile) need */
-    bool pend = false;
-#if SBLAS_W_DEFER
-    unsigned wpar = 0;       /* phase parity per border mbarrier */
-#endif
-    int p_info = 0, p_j = 0, p_row = 0;          /* info = ring | parity << 3 | ext << 4 | k << 5 */
-    double p_mine = 0.0, p_yv = 0.0;
-    auto settle = [&](bool wait) {
-        const int p_ring = p_info & 7, p_k = p_info >> 5;
-        const bool p_ext = (p_info & 16) != 0;
-        if (wait) mbar_wait(wcbar0 + 8u * p_ring, (uint32_t)(p_info >> 3) & 1u);   /* all eight warps have posted their pieces */
-        const double *WC = red + (kRing * 2 * kCWarps) + p_ring * (3 * kCWarps);   /* [WC | WCend | WT] x 8 */
+    /* path W, after the tile's barrier: lane 4k of a warp finishes the row that left its chunk, warp 0
+     * the row left open by the previous tile.  (Settling one tile later on an mbarrier instead of a
+     * block barrier was measured slower: warps drift apart and the stage ring turns over unevenly.) */
+    auto settle = [&](const double *WC, int p_j, int p_k, bool p_ext, int p_row, double p_mine, double p_yv) {
         if (p_k > 0 && lane == 4 * p_k) {                       /* the row that left my chunk */
             double tot = p_mine;
             bool closed_in_tile = false;
@@ -291,7 +275,6 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
             }
             a.carry[p_j] = tot;
         }
-        pend = false;
     };
 
     mbar_wait(full0 + 8u * s, 0u);
@@ -313,9 +296,6 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
         const uint32_t eb = empty0 + 8u * s;
         const int nseg = nown + 1;                 /* segment 0 = the row left open by the previous tile */
 
-#if SBLAS_W_DEFER
-        if (pend && !((m.w & 6) == 4 && (a.mode & 1) == 0)) settle(true);   /* W tiles settle after their gather */
-#endif
 
         if (nown <= 1) {
             /* ---- A: at most one row starts here: block reduction straight from registers */
@@ -392,11 +372,10 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
          * warp walks its 8 slices of 32 consecutive entries, every lane adds its product to the
          * running piece and parks its partial sum in the warp's scratch (P[piece][lane]) wherever a
          * row starts; ONE transposed pass then finishes all pieces at once (lanes 4c..4c+3 sum piece
-         * c: 8 loads, a 3-level tree, 2 shuffles) -- no flags, no scan, no per-piece shuffle chain, and
-         * the stage goes back to the producer before the sums start.  Piece 0 belongs to the row open
+         * c: 8 loads, a 3-level tree, 2 shuffles) -- no flags, no scan, no per-piece shuffle chain.
+         * The scratch is the warp's own, already consumed slice of val.  Piece 0 belongs to the row open
          * at the chunk start, the last piece to the row that leaves the chunk; they meet the
-         * neighbours' pieces in shared memory, and that is settled during the NEXT tile (settle(),
-         * an mbarrier the eight warps arrive on), so no warp ever waits for the slowest one here. */
+         * neighbours' pieces in shared memory after the tile's one barrier (settle()). */
         if ((m.w & 6) == 4 && (a.mode & 1) == 0) {
             const unsigned short *qw = reinterpret_cast<const unsigned short *>(&S.meta2);
             const int qa = qw[warp];
@@ -408,15 +387,7 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
                 const int r = S.rp[S.rp_off + qa + lane];         /* always staged: 2 <= nown <= 56 rows */
                 v = min(max(r, base + clo), base + chi) - base - c0;
             }
-#if SBLAS_W_SHUFFLE
-            release_stage(eb, lane);                             /* the stage is not touched again */
-#elif SBLAS_W_SCRATCH
-            release_stage(eb, lane);                             /* the stage is not touched again */
-            double *pieces = reinterpret_cast<double *>(smem + kStages * sizeof(Stage) + kBarBytes) +
-                             kGroups * kRedDoubles + (grp * kCWarps + warp) * kScratchDoubles;
-#else
             double *pieces = S.val + c0;                         /* scratch: my own (consumed) slice of val */
-#endif
             /* piece c is finished by lanes 4c..4c+3; lane 4c, c in [1,k], owns row rs+qa+c-1 */
             const int pc = lane >> 2;
             const int myrow = rs + qa + pc - 1;
@@ -427,9 +398,6 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
                 mbar_wait(full0 + 8u * sn, phn);
                 gather(st[sn], base + step);
             }
-#if SBLAS_W_DEFER
-            if (pend) settle(true);                              /* the previous tile's chunk borders */
-#endif
             double acc = 0.0, mine = 0.0;
             int cur = 0;
             int nb = __shfl_sync(kFull, v, 0);                   /* next row start (chunk-local), 256 = none */
@@ -442,11 +410,7 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
                 while (nb < 32 * (i + 1)) {                      /* a row starts inside slice i */
                     const int o = nb - 32 * i;
                     if (lane >= lo_lane && lane < o) acc += p[i];
-#if SBLAS_W_SHUFFLE
-                    { const double tot = warp_sum(acc); if (pc == cur) mine = tot; }
-#else
                     pieces[cur * 32 + lane] = acc;
-#endif
                     acc = 0.0;
                     lo_lane = o;
                     ++cur;
@@ -454,9 +418,6 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
                 }
                 if (lane >= lo_lane) acc += p[i];
             }
-#if SBLAS_W_SHUFFLE
-            { const double tot = warp_sum(acc); if (pc == cur) mine = tot; }
-#else
             pieces[cur * 32 + lane] = acc;                       /* the piece that leaves the chunk: cur == k */
             __syncwarp();
             {
@@ -470,11 +431,8 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
                 mine += __shfl_xor_sync(kFull, mine, 1);
                 mine += __shfl_xor_sync(kFull, mine, 2);         /* pieces beyond k: unused garbage */
             }
-#if !SBLAS_W_SCRATCH
             fence_proxy_async_smem();          /* generic writes to the slot before the next bulk copy */
             release_stage(eb, lane);
-#endif
-#endif
             if (owner && pc < k) {             /* rows that start and end inside my chunk */
                 if (myrow == a.skip_first) a.edge[0] = mine;
                 else if (myrow == a.skip_last) a.edge[1] = mine;
@@ -483,19 +441,8 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
             double *WC = red + (kRing * 2 * kCWarps) + ring * (3 * kCWarps);   /* [WC | WCend | WT] x 8 */
             if (lane == 0) { WC[warp] = mine; WC[kCWarps + warp] = k > 0 ? 1.0 : 0.0; }
             if (lane == 4 * k) WC[2 * kCWarps + warp] = mine;
-#if SBLAS_W_DEFER
-            __syncwarp();
-            if (lane == 0) mbar_arrive(wcbar0 + 8u * ring);
-            pend = true;
-            p_info = ring | (int)((wpar >> ring) & 1u) << 3 | (ext ? 16 : 0) | k << 5;
-            wpar ^= 1u << ring;
-            p_j = j; p_row = myrow; p_mine = mine; p_yv = yv;
-#else
             named_bar_sync(bar_id, kConsumers);
-            p_info = ring | (ext ? 16 : 0) | k << 5;
-            p_j = j; p_row = myrow; p_mine = mine; p_yv = yv;
-            settle(false);
-#endif
+            settle(WC, j, k, ext, myrow, mine, yv);
             s = sn; ph = phn; ++it;
             continue;
         }
@@ -689,9 +636,6 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
         release_stage(eb, lane);
         s = sn; ph = phn; ++it;
     }
-#if SBLAS_W_DEFER
-    if (pend) settle(true);                    /* the last tile's chunk borders */
-#endif
 }
 
 int g_sm_count[64] = {0};
