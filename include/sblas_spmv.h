@@ -183,6 +183,13 @@ int sblas_spmv_plan_exchange_merge_phase(sblas_spmv_plan *plan, double alpha, do
 double sblas_spmv_plan_alg_bytes(const sblas_spmv_plan *plan, int beta_nonzero, long long x_touched_per_gpu);
 /* number of kernel launches one execute enqueues (all GPUs of the plan) */
 int sblas_spmv_plan_launches(const sblas_spmv_plan *plan);
+/* Row panels (one kernel launch each; adaptive row binning, sblas_plan.c).  unit i ->
+ * out = {local segment, kernel kind (SBLAS_K_*), ipt / R | window << 8, first row, last row
+ *        (global, inclusive), first entry, one-past-last entry (global), launches}. */
+int sblas_spmv_plan_num_units(const sblas_spmv_plan *plan);
+int sblas_spmv_plan_unit(const sblas_spmv_plan *plan, int i, long long out[8]);
+/* launch ONE panel's kernel(s) on its stream (measurement: time a kernel alone) */
+int sblas_spmv_plan_execute_unit(sblas_spmv_plan *plan, int i, double alpha, double beta);
 void sblas_spmv_plan_destroy(sblas_spmv_plan *plan);
 
 const char *sblas_last_error(void);

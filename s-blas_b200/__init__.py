@@ -111,6 +111,9 @@ def lib():
     L.sblas_spmv_plan_alg_bytes.argtypes = [_vp, C.c_int, _LL]
     L.sblas_spmv_plan_alg_bytes.restype = C.c_double
     L.sblas_spmv_plan_launches.argtypes = [_vp]
+    L.sblas_spmv_plan_num_units.argtypes = [_vp]
+    L.sblas_spmv_plan_unit.argtypes = [_vp, C.c_int, P(_LL)]
+    L.sblas_spmv_plan_execute_unit.argtypes = [_vp, C.c_int, C.c_double, C.c_double]
     L.sblas_spmv_plan_destroy.argtypes = [_vp]
     L.sblas_spmv_plan_destroy.restype = None
     L.sblas_last_error.restype = C.c_char_p
@@ -381,6 +384,21 @@ class Plan:
     @property
     def launches(self):
         return lib().sblas_spmv_plan_launches(self._h)
+
+    def units(self):
+        """Row panels of the plan (one kernel each): list of dicts."""
+        out = []
+        for i in range(lib().sblas_spmv_plan_num_units(self._h)):
+            b = (_LL * 8)()
+            assert lib().sblas_spmv_plan_unit(self._h, i, b) == 0
+            out.append(dict(index=i, segment=int(b[0]), kind=int(b[1]), ipt=int(b[2]), row_lo=int(b[3]), row_hi=int(b[4]),
+                            nz0=int(b[5]), nz1=int(b[6]), launches=int(b[7])))
+        return out
+
+    def execute_unit(self, i, alpha, beta):
+        rc = lib().sblas_spmv_plan_execute_unit(self._h, int(i), float(alpha), float(beta))
+        if rc != 0:
+            raise RuntimeError("execute_unit failed: %s" % last_error())
 
     def destroy(self):
         if self._h:

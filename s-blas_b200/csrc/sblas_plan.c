@@ -1062,6 +1062,48 @@ double sblas_spmv_plan_alg_bytes(const sblas_spmv_plan *P, int beta_nonzero, lon
     return b;
 }
 
+int sblas_spmv_plan_num_units(const sblas_spmv_plan *P) { return P->nunits; }
+
+static const sblas_seg *unit_segment(const sblas_spmv_plan *P, int i, int *sidx)
+{
+    for (int s = 0; s < P->nseg; ++s)
+        if (i >= P->segs[s].unit_begin && i < P->segs[s].unit_end) { if (sidx) *sidx = s; return &P->segs[s]; }
+    return NULL;
+}
+
+int sblas_spmv_plan_unit(const sblas_spmv_plan *P, int i, long long out[8])
+{
+    int sidx = 0;
+    if (i < 0 || i >= P->nunits) return -1;
+    const sblas_seg *S = unit_segment(P, i, &sidx);
+    if (!S) return -1;
+    const sblas_unit *U = &P->units[i];
+    const sblas_dev *D = &P->devs[S->dev];
+    out[0] = sidx; out[1] = U->kind; out[2] = U->ipt;
+    out[3] = (long long)D->first_row + U->args.row_lo;
+    out[4] = (long long)D->first_row + U->args.row_hi;
+    out[5] = D->first_idx + U->args.nz0;
+    out[6] = D->first_idx + U->args.nz1;
+    out[7] = ((U->kind == SBLAS_K_TMA || U->kind == SBLAS_K_TILE) && U->args.ntile > 0) ? 2 : 1;
+    return 0;
+}
+
+int sblas_spmv_plan_execute_unit(sblas_spmv_plan *P, int i, double alpha, double beta)
+{
+    int rc = 0;
+    if (i < 0 || i >= P->nunits || P->dry) return -1;
+    const sblas_seg *S = unit_segment(P, i, NULL);
+    if (!S) return -1;
+    sblas_unit *U = &P->units[i];
+    sblas_dev *D = &P->devs[S->dev];
+    CU(cudaSetDevice(D->device));
+    U->args.alpha = alpha; U->args.beta = beta;
+    U->args.edge = S->args.edge;
+    CU(sblas_launch_spmv_segment(&U->args, U->kind, U->ipt, 0, D->streams[S->stream]));
+fail:
+    return rc;
+}
+
 int sblas_spmv_plan_launches(const sblas_spmv_plan *P)
 {
     int n = 0;
