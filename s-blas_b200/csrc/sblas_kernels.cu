@@ -86,27 +86,58 @@ __global__ void __launch_bounds__(kThreads) spmv_vec_kernel(const sblas_seg_args
  * of a thread is independent of its neighbours', 2048 threads per SM keep ~70 KB in flight, and
  * the row pointer / y accesses of a warp are 128 / 256 contiguous bytes.  Rows of exactly two
  * entries on an even offset take val and col as one 16-byte and one 8-byte load. */
-__global__ void __launch_bounds__(kThreads, 8) spmv_short_kernel(const sblas_seg_args a)
+constexpr int kShortRows = 2;         /* rows per thread: two independent load chains in flight */
+__global__ void __launch_bounds__(kThreads, 6) spmv_short_kernel(const sblas_seg_args a)
 {
-    const long long gid = (long long)blockIdx.x * kThreads + threadIdx.x;
-    if (gid > (long long)a.row_hi - a.row_lo) return;
-    const int r = a.row_lo + (int)gid;
-    const int lo = max(__ldg(a.rowptr + r), a.nz0);
-    const int hi = min(__ldg(a.rowptr + r + 1), a.nz1);
-    const bool edge = (r == a.skip_first) || (r == a.skip_last);
-    double yv = 0.0;
-    if (a.beta != 0.0 && !edge) yv = a.y[r];
-    double acc = 0.0;
-    if (hi - lo == 2 && (lo & 1) == 0) {
-        const double2 v = __ldg(reinterpret_cast<const double2 *>(a.val + lo));
-        const int2 c = __ldg(reinterpret_cast<const int2 *>(a.col + lo));
-        acc = fma(v.y, __ldg(a.x + c.y), v.x * __ldg(a.x + c.x));
-    } else {
-        for (int k = lo; k < hi; ++k) acc = fma(__ldg(a.val + k), __ldg(a.x + __ldg(a.col + k)), acc);
+    const long long nrows = (long long)a.row_hi - a.row_lo + 1;
+    const long long g0 = (long long)blockIdx.x * (kThreads * kShortRows) + threadIdx.x;
+    int r[kShortRows], lo[kShortRows], hi[kShortRows];
+    bool live[kShortRows];
+    double yv[kShortRows], acc[kShortRows];
+#pragma unroll
+    for (int u = 0; u < kShortRows; ++u) {          /* row u of this thread: consecutive threads, consecutive rows */
+        const long long g = g0 + (long long)u * kThreads;
+        live[u] = g < nrows;
+        r[u] = a.row_lo + (int)(live[u] ? g : 0);
+        lo[u] = 0; hi[u] = 0;
+        if (live[u]) {
+            lo[u] = max(__ldg(a.rowptr + r[u]), a.nz0);
+            hi[u] = min(__ldg(a.rowptr + r[u] + 1), a.nz1);
+        }
     }
-    if (r == a.skip_first) a.edge[0] = acc;
-    else if (r == a.skip_last) a.edge[1] = acc;
-    else a.y[r] = a.alpha * acc + a.beta * yv;
+#pragma unroll
+    for (int u = 0; u < kShortRows; ++u) {
+        yv[u] = 0.0;
+        if (live[u] && a.beta != 0.0 && r[u] != a.skip_first && r[u] != a.skip_last) yv[u] = a.y[r[u]];
+    }
+    /* rows of exactly two entries on an even offset: one 16-byte and one 8-byte load each */
+    bool pair[kShortRows];
+    double2 v2[kShortRows];
+    int2 c2[kShortRows];
+#pragma unroll
+    for (int u = 0; u < kShortRows; ++u) {
+        pair[u] = (hi[u] - lo[u] == 2) && ((lo[u] & 1) == 0);
+        if (pair[u]) {
+            v2[u] = __ldg(reinterpret_cast<const double2 *>(a.val + lo[u]));
+            c2[u] = __ldg(reinterpret_cast<const int2 *>(a.col + lo[u]));
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kShortRows; ++u) {
+        acc[u] = 0.0;
+        if (pair[u]) {
+            acc[u] = fma(v2[u].y, __ldg(a.x + c2[u].y), v2[u].x * __ldg(a.x + c2[u].x));
+        } else {
+            for (int k = lo[u]; k < hi[u]; ++k) acc[u] = fma(__ldg(a.val + k), __ldg(a.x + __ldg(a.col + k)), acc[u]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kShortRows; ++u) {
+        if (!live[u]) continue;
+        if (r[u] == a.skip_first) a.edge[0] = acc[u];
+        else if (r[u] == a.skip_last) a.edge[1] = acc[u];
+        else a.y[r[u]] = a.alpha * acc[u] + a.beta * yv[u];
+    }
 }
 
 /* ------------------------------------------------------------------ pipelined vector kernel
@@ -672,7 +703,7 @@ extern "C" cudaError_t sblas_launch_spmv_segment(const sblas_seg_args *a, int ki
     if (kind == SBLAS_K_VECP) return ipt == 4 ? launch_vecp<4>(a, s) : launch_vecp<8>(a, s);
     if (kind == SBLAS_K_ROWTILE) return sblas_launch_rowtile(a, ipt & 0xff, ipt >> 8, s);
     if (kind == SBLAS_K_SHORT) {
-        spmv_short_kernel<<<(unsigned)((nrows + kThreads - 1) / kThreads), kThreads, 0, s>>>(*a);
+        spmv_short_kernel<<<(unsigned)((nrows + kThreads * kShortRows - 1) / (kThreads * kShortRows)), kThreads, 0, s>>>(*a);
         return cudaGetLastError();
     }
     if (kind == SBLAS_K_TMA && nnz > 0 && a->ntile > 0) {
