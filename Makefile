@@ -13,7 +13,7 @@ CFLAGS := -O2 -fPIC -Wall -Wno-unused-function -std=gnu11 $(INC)
 NVFLAGS := $(ARCH) -O3 -lineinfo -Xptxas -v -Xcompiler -fPIC $(INC)
 
 OBJS := $(OUT)/sblas_kernels.o $(OUT)/sblas_spmv_tma.o $(OUT)/sblas_spmv_rowtile.o $(OUT)/sblas_synth.o $(OUT)/sblas_partition.o $(OUT)/sblas_plan.o \
-        $(OUT)/sblas_api.o $(OUT)/sblas_shim.o
+        $(OUT)/sblas_api.o $(OUT)/sblas_ingest.o $(OUT)/sblas_shim.o
 
 all: $(OUT)/libsblas_spmv.so test_spmv oracle
 

@@ -214,3 +214,36 @@ def load_mtx(path, mode="f"):
     L.oracle_load_mtx(path.encode(), mode.encode(), C.byref(m), C.byref(n), C.byref(nz),
                       r.ctypes.data, c.ctypes.data, v.ctypes.data)
     return m.value, n.value, r, c, v
+
+
+def load_mtx_csr(path):
+    """CPU restatement (numpy) of the reference's CORRECT loader, sptrsv/sptrsv_v1/src/
+    mmio_highlevel.h:139-298 (mmio_data): entries bucketed by row in file order, off-diagonal
+    entries of symmetric / hermitian files mirrored right after their original with the same value,
+    pattern -> 1.0, integer converted, complex -> real part.  Checker for include/sblas_ingest.h
+    (SURVEY.md section 8f-1).  Returns (m, n, rowptr int64, col int32, val float64, is_symmetric)."""
+    with open(path) as f:
+        banner = f.readline().split()
+        if len(banner) != 5 or not banner[0].startswith("%%MatrixMarket"):
+            raise IOError("bad banner")
+        field, symm = banner[3].lower(), banner[4].lower()
+        line = f.readline()
+        while line.startswith("%"):
+            line = f.readline()
+        m, n, listed = (int(t) for t in line.split()[:3])
+        sym = symm in ("symmetric", "hermitian")            # mmio_highlevel.h:174-178
+        rows, cols, vals = [], [], []
+        toks = f.read().split()
+    per = {"pattern": 2, "complex": 4}.get(field, 3)
+    for e in range(listed):
+        t = toks[per * e: per * e + per]
+        i, j = int(t[0]) - 1, int(t[1]) - 1
+        v = 1.0 if field == "pattern" else float(t[2])
+        rows.append(i); cols.append(j); vals.append(v)
+        if sym and i != j:                                  # mirrored entry follows its original (:254-266)
+            rows.append(j); cols.append(i); vals.append(v)
+    rows = np.asarray(rows, np.int64)
+    order = np.argsort(rows, kind="stable")                 # bucket by row, file order kept inside a row
+    rp = np.zeros(m + 1, np.int64)
+    np.cumsum(np.bincount(rows, minlength=m), out=rp[1:])
+    return m, n, rp, np.asarray(cols, np.int32)[order], np.asarray(vals, np.float64)[order], sym

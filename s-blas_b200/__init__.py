@@ -112,6 +112,8 @@ def lib():
     L.sblas_spmv_plan_alg_bytes.restype = C.c_double
     L.sblas_spmv_plan_launches.argtypes = [_vp]
     L.sblas_spmv_plan_num_units.argtypes = [_vp]
+    L.sblas_mtx_info.argtypes = [C.c_char_p, P(C.c_int), P(C.c_int), P(_LL), P(C.c_int)]
+    L.sblas_mtx_read_csr.argtypes = [C.c_char_p, _vp, _vp, _vp]
     L.sblas_spmv_plan_unit.argtypes = [_vp, C.c_int, P(_LL)]
     L.sblas_spmv_plan_execute_unit.argtypes = [_vp, C.c_int, C.c_double, C.c_double]
     L.sblas_spmv_plan_destroy.argtypes = [_vp]
@@ -410,6 +412,23 @@ class Plan:
             self.destroy()
         except Exception:
             pass
+
+
+def mtx_read_csr(path):
+    """Correct Matrix-Market -> CSR ingest (include/sblas_ingest.h; opt-in):
+    returns (m, n, rowptr int64, col int32, val float64, is_symmetric)."""
+    m, n, nnz, sym = C.c_int(), C.c_int(), _LL(), C.c_int()
+    rc = lib().sblas_mtx_info(path.encode(), C.byref(m), C.byref(n), C.byref(nnz), C.byref(sym))
+    if rc != 0:
+        raise IOError("sblas_mtx_info(%s) = %d" % (path, rc))
+    rp = np.zeros(m.value + 1, np.int64)
+    col = np.zeros(max(nnz.value, 1), np.int32)[:nnz.value]
+    val = np.zeros(max(nnz.value, 1), np.float64)[:nnz.value]
+    rc = lib().sblas_mtx_read_csr(path.encode(), rp.ctypes.data, col.ctypes.data if nnz.value else None,
+                                  val.ctypes.data if nnz.value else None)
+    if rc != 0:
+        raise IOError("sblas_mtx_read_csr(%s) = %d" % (path, rc))
+    return m.value, n.value, rp, col, val, bool(sym.value)
 
 
 def memcpy(dst, src, nbytes, kind):

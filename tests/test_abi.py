@@ -22,7 +22,7 @@ def _declared(header):
 def test_library_exports_every_declared_symbol():
     L = sb.lib()
     names = _declared("sblas_spmv.h") + _declared("sblas_device.h") + _declared("sblas_synth.h") + \
-        _declared("spmv_kernel.h")
+        _declared("sblas_ingest.h") + _declared("spmv_kernel.h")
     assert len(names) > 40
     for n in names:
         assert hasattr(L, n), "missing export: " + n

@@ -61,6 +61,29 @@ def test_cli_file_mode(qh768, tmp_path):
         assert ("Loading input matrix from " + mtx) in out
 
 
+def test_cli_correct_ingest_opt_in(tmp_path):
+    """SBLAS_INGEST=csr: a SYMMETRIC, unsorted file is expanded and bucketed by
+    row; the m:/nnz line shows the expanded count and all three entry points agree (Y Y)."""
+    rng = np.random.default_rng(9)
+    m = 300
+    ents = {}
+    for _ in range(4000):
+        i, j = sorted((int(rng.integers(0, m)), int(rng.integers(0, m))), reverse=True)
+        ents[(i, j)] = float(rng.uniform(0.5, 1.5))
+    items = list(ents.items())
+    rng.shuffle(items)
+    mtx = str(tmp_path / "sym.mtx")
+    with open(mtx, "w") as fh:
+        fh.write("%%MatrixMarket matrix coordinate real symmetric\n%d %d %d\n" % (m, m, len(items)))
+        for (i, j), v in items:
+            fh.write("%d %d %r\n" % (i + 1, j + 1, v))
+    expanded = sum(2 if i != j else 1 for (i, j), _ in items)
+    p = subprocess.run([CLI, "f", mtx, "1", "2", "1", "f"], capture_output=True, text=True, timeout=300, cwd=ROOT,
+                       env=dict(os.environ, SBLAS_INGEST="csr"))
+    assert p.returncode == 0, p.stdout
+    check_output(p.stdout, m, m, expanded, 2, 1, 1)
+
+
 def test_cli_generator_mode():
     rc, out = run([CLI, "g", "200", "1", "1", "1"])          # spmv/INSTALL.md:78
     assert rc == 0, out

@@ -1,0 +1,107 @@
+"""the opt-in correct Matrix-Market -> CSR ingest
+(include/sblas_ingest.h) against the oracle's restatement of the reference's own correct loader
+(sptrsv/sptrsv_v1/src/mmio_highlevel.h:139-298) and against scipy.io.mmread."""
+import os
+
+import numpy as np
+import pytest
+import scipy.io
+import scipy.sparse
+
+import oracle
+import sblas_b200 as sb
+from conftest import GOLDEN
+
+
+def write_mtx(path, m, n, entries, field="real", symm="general", comments=2):
+    with open(path, "w") as f:
+        f.write("%%%%MatrixMarket matrix coordinate %s %s\n" % (field, symm))
+        for k in range(comments):
+            f.write("%% comment %d\n" % k)
+        f.write("%d %d %d\n" % (m, n, len(entries)))
+        for e in entries:
+            if field == "pattern":
+                f.write("%d %d\n" % (e[0] + 1, e[1] + 1))
+            elif field == "integer":
+                f.write("%d %d %d\n" % (e[0] + 1, e[1] + 1, int(e[2])))
+            elif field == "complex":
+                f.write("%d %d %.17g %.17g\n" % (e[0] + 1, e[1] + 1, e[2], 0.25))
+            else:
+                f.write("%d %d %.17g\n" % (e[0] + 1, e[1] + 1, e[2]))
+
+
+def dense(m, n, rp, col, val):
+    a = np.zeros((m, n))
+    rows = np.repeat(np.arange(m), np.diff(rp))
+    np.add.at(a, (rows, col), val)
+    return a
+
+
+CASES = [("real", "general"), ("real", "symmetric"), ("pattern", "general"), ("pattern", "symmetric"),
+         ("integer", "general"), ("integer", "symmetric"), ("complex", "hermitian")]
+
+
+@pytest.mark.parametrize("field,symm", CASES)
+def test_ingest_matches_oracle_and_scipy(tmp_path, field, symm):
+    rng = np.random.default_rng(hash((field, symm)) % 1000)
+    m = n = 37
+    ents = {}
+    for _ in range(260):
+        i, j = int(rng.integers(0, m)), int(rng.integers(0, n))
+        if symm != "general" and j > i:
+            i, j = j, i                              # lower triangle only, as the format requires
+        ents[(i, j)] = float(rng.integers(-9, 10)) if field == "integer" else float(rng.standard_normal())
+    entries = [(i, j, v) for (i, j), v in ents.items()]
+    rng.shuffle(entries)                             # unsorted file: the case the harness loader gets wrong
+    path = str(tmp_path / "a.mtx")
+    write_mtx(path, m, n, entries, field, symm)
+    gm, gn, rp, col, val, sym = sb.mtx_read_csr(path)
+    om, on, orp, ocol, oval, osym = oracle.load_mtx_csr(path)
+    assert (gm, gn, sym) == (om, on, osym) == (m, n, symm != "general")
+    assert (rp == orp).all() and (col == ocol).all() and (val == oval).all()      # entry for entry
+    assert rp[0] == 0 and rp[-1] == len(col) and (np.diff(rp) >= 0).all()
+    if field != "complex":                           # scipy conjugates hermitian mirrors; the reference does not
+        want = scipy.io.mmread(path).toarray()
+        assert np.array_equal(dense(m, n, rp, col, val), want)
+
+
+def test_ingest_equals_harness_loader_on_row_sorted_general_file(tmp_path):
+    """For a general file whose entries are sorted by row the correct loader and the reference
+    harness's loader (file order used as CSR) give the same arrays."""
+    rng = np.random.default_rng(5)
+    m, n = 50, 41
+    entries = sorted(((int(i), int(j), float(rng.standard_normal())) for i, j in
+                      {(int(rng.integers(0, m)), int(rng.integers(0, n))) for _ in range(300)}), key=lambda e: e[0])
+    path = str(tmp_path / "s.mtx")
+    write_mtx(path, m, n, entries)
+    _, _, rp, col, val, _ = sb.mtx_read_csr(path)
+    hm, hn, hr, hc, hv = oracle.load_mtx(path, "f")
+    assert (rp == oracle.coo_to_rowptr(hm, hr)).all() and (col == hc).all() and (val == hv).all()
+
+
+def test_ingest_errors(tmp_path):
+    p = str(tmp_path / "bad.mtx")
+    open(p, "w").write("not a banner\n1 1 1\n1 1 1.0\n")
+    with pytest.raises(IOError):
+        sb.mtx_read_csr(p)
+    with pytest.raises(IOError):
+        sb.mtx_read_csr(str(tmp_path / "missing.mtx"))
+    open(p, "w").write("%%MatrixMarket matrix coordinate real general\n3 3 4\n1 1 1.0\n2 2 2.0\n")
+    with pytest.raises(IOError):
+        sb.mtx_read_csr(p)                           # fewer entries than announced
+    open(p, "w").write("%%MatrixMarket matrix coordinate real general\n3 3 1\n4 1 1.0\n")
+    with pytest.raises(IOError):
+        sb.mtx_read_csr(p)                           # row index out of range
+
+
+def test_sample_matrix_through_the_correct_loader():
+    """qh768 is a `general` file sorted by COLUMN: the harness loader yields a permuted matrix
+    (SURVEY F3), the correct loader the matrix scipy reads."""
+    path = os.path.join(GOLDEN, "..", "..", "sample_matrix", "qh768.mtx")
+    if not os.path.exists(path):
+        path = "/root/reference/sample_matrix/qh768.mtx"
+    if not os.path.exists(path):
+        pytest.skip("sample matrix not present")
+    m, n, rp, col, val, sym = sb.mtx_read_csr(path)
+    assert (m, n, int(rp[-1]), sym) == (768, 768, 2934, False)
+    assert np.array_equal(dense(m, n, rp, col, val), scipy.io.mmread(path).toarray())
