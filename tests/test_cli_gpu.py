@@ -74,7 +74,8 @@ def test_cli_correct_ingest_opt_in(tmp_path):
     rng.shuffle(items)
     mtx = str(tmp_path / "sym.mtx")
     with open(mtx, "w") as fh:
-        fh.write("%%MatrixMarket matrix coordinate real symmetric\n%d %d %d\n" % (m, m, len(items)))
+        fh.write("%%MatrixMarket matrix coordinate real symmetric\n")
+        fh.write("%d %d %d\n" % (m, m, len(items)))
         for (i, j), v in items:
             fh.write("%d %d %r\n" % (i + 1, j + 1, v))
     expanded = sum(2 if i != j else 1 for (i, j), _ in items)
