@@ -210,6 +210,20 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas
 #pragma unroll
             for (int i = 3; i < NS; i += 2) t1 += p[i];
             mine = warp_sum(t + t1);
+        } else if (R == 2) {
+            /* two rows: two accumulators split at the second row's start, two interleaved reductions */
+            const int bnd = __shfl_sync(kFull, cv, 0) - lane;     /* slot i belongs to row 0 iff 32*i < bnd */
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                if (32 * i < bnd) a0 += p[i]; else a1 += p[i];
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                a0 += __shfl_xor_sync(kFull, a0, off);
+                a1 += __shfl_xor_sync(kFull, a1, off);
+            }
+            mine = pc == 0 ? a0 : a1;
         } else {
             double acc = 0.0;
             int cur = 0;
