@@ -120,6 +120,10 @@ int sblas_spmv_plan_execute(sblas_spmv_plan *plan, const double *alpha, const do
  * host y and waits for the plan's GPUs. */
 int sblas_spmv_plan_upload(sblas_spmv_plan *plan, const double *x, const double *y);
 int sblas_spmv_plan_download(sblas_spmv_plan *plan, double *y);
+/* Iterative use (y -> x chaining): x <- y on every GPU of the plan, on the
+ * devices only (NVLink all-gather of the row slices each GPU owns, event-ordered, no host wait).
+ * Square matrices; in-process plans (or a single-rank plan).  Follow with execute_device. */
+int sblas_spmv_plan_chain(sblas_spmv_plan *plan);
 
 /* Device-resident execute: x and y already sit in the plan's device buffers
  * (see sblas_spmv_plan_x / _y); nothing crosses PCIe.  Enqueues on the plan's

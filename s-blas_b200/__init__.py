@@ -112,6 +112,7 @@ def lib():
     L.sblas_spmv_plan_alg_bytes.restype = C.c_double
     L.sblas_spmv_plan_launches.argtypes = [_vp]
     L.sblas_spmv_plan_num_units.argtypes = [_vp]
+    L.sblas_spmv_plan_chain.argtypes = [_vp]
     L.sblas_mtx_info.argtypes = [C.c_char_p, P(C.c_int), P(C.c_int), P(_LL), P(C.c_int)]
     L.sblas_mtx_read_csr.argtypes = [C.c_char_p, _vp, _vp, _vp]
     L.sblas_spmv_plan_unit.argtypes = [_vp, C.c_int, P(_LL)]
@@ -299,6 +300,12 @@ class Plan:
         rc = lib().sblas_spmv_plan_execute_device(self._h, alpha, beta, 1 if sync else 0)
         if rc != 0:
             raise RuntimeError("sblas_spmv_plan_execute_device rc=%d: %s" % (rc, last_error()))
+
+    def chain(self):
+        """x <- y on every GPU of the plan (device-side all-gather over NVLink); then execute_device."""
+        rc = lib().sblas_spmv_plan_chain(self._h)
+        if rc != 0:
+            raise RuntimeError("chain failed: %s" % last_error())
 
     def merge_gathered(self, gathered_ptr, alpha, beta):
         rc = lib().sblas_spmv_plan_merge_gathered(self._h, int(gathered_ptr), alpha, beta)

@@ -38,6 +38,7 @@ typedef struct sblas_dev {
     int *h_mrow, *h_mbeg; const double **h_msrc; long long *h_msrc_off;
     cudaStream_t *streams; int nstreams;
     cudaEvent_t *ev_seg, ev_in, ev_done;
+    cudaEvent_t ev_y, ev_chain;       /* y complete on this GPU / this GPU has pulled every y slice (chain) */
     int kind, ipt;
     long long xs_lo, xs_hi;           /* slice of x this GPU uploads itself */
 } sblas_dev;

@@ -120,6 +120,8 @@ static void free_dev(sblas_dev *D, int dry)
     }
     if (D->ev_in) cudaEventDestroy(D->ev_in);
     if (D->ev_done) cudaEventDestroy(D->ev_done);
+    if (D->ev_y) cudaEventDestroy(D->ev_y);
+    if (D->ev_chain) cudaEventDestroy(D->ev_chain);
     free(D->streams); free(D->ev_seg);
     free(D->h_mrow); free(D->h_mbeg); free(D->h_msrc); free(D->h_msrc_off);
 }
@@ -377,6 +379,8 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
         }
         CU(cudaEventCreateWithFlags(&D->ev_in, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&D->ev_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&D->ev_y, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&D->ev_chain, cudaEventDisableTiming));
         cudaStream_t st = D->streams[0];
         (void)st;
 
@@ -858,6 +862,63 @@ int sblas_spmv_plan_download(sblas_spmv_plan *P, double *y)
         if (D->seg_begin < 0) continue;
         CU(cudaSetDevice(D->device));
         CU(cudaStreamSynchronize(D->streams[0]));
+    }
+fail:
+    return rc;
+}
+
+/* rows of y a GPU owns (a split first row belongs to the GPU where the row starts): skip = 0 or 1 */
+static int owned_skip(const sblas_spmv_plan *P, int d)
+{
+    const sblas_dev *D = &P->devs[d];
+    const sblas_seg *S0 = &P->segs[D->seg_begin];
+    if (!P->g_sf[S0->gidx]) return 0;
+    const int og = row_owner_seg(P, S0->gidx);
+    const int od = P->rank_mode ? (P->g_owner[og] == P->rank ? 0 : -1) : P->g_owner[og];
+    return od != d;
+}
+
+/* Iterative use: x <- y on every GPU of the plan, entirely on the devices.
+ * Every GPU pulls the rows each GPU owns out of that GPU's y slice into its own replica of x --
+ * an all-gather over NVLink (cudaMemcpyPeerAsync), ordered by events only; the host does not
+ * wait.  Needs a square matrix; plans that hold one shard of a multi-process job (world > 1)
+ * gather through the caller's collective instead. */
+int sblas_spmv_plan_chain(sblas_spmv_plan *P)
+{
+    int rc = 0;
+    if (P->dry || P->m != P->n || (P->rank_mode && P->world > 1)) {
+        sblas_set_error("%s%s (line %d)", "chain needs a square matrix and every shard in this process", "", __LINE__);
+        return -1;
+    }
+    const int nd = P->ndev;
+    for (int d = 0; d < nd; ++d) {
+        sblas_dev *D = &P->devs[d];
+        if (D->seg_begin < 0) continue;
+        CU(cudaSetDevice(D->device));
+        CU(cudaEventRecord(D->ev_y, D->streams[0]));             /* everything enqueued so far: y is final */
+    }
+    for (int d = 0; d < nd; ++d) {
+        sblas_dev *D = &P->devs[d];
+        if (D->seg_begin < 0) continue;
+        CU(cudaSetDevice(D->device));
+        for (int o = 0; o < nd; ++o) {
+            sblas_dev *O = &P->devs[o];
+            if (O->seg_begin < 0) continue;
+            const int skip = owned_skip(P, o);
+            if (O->rows - skip <= 0) continue;
+            if (o != d) CU(cudaStreamWaitEvent(D->streams[0], O->ev_y, 0));
+            CU(cudaMemcpyPeerAsync(D->d_x + O->first_row + skip, D->device, O->d_y + skip, O->device,
+                                   (size_t)(O->rows - skip) * sizeof(double), D->streams[0]));
+        }
+        CU(cudaEventRecord(D->ev_chain, D->streams[0]));
+    }
+    /* nobody overwrites its y (next product) before every GPU has pulled it */
+    for (int o = 0; o < nd; ++o) {
+        sblas_dev *O = &P->devs[o];
+        if (O->seg_begin < 0) continue;
+        CU(cudaSetDevice(O->device));
+        for (int d = 0; d < nd; ++d)
+            if (d != o && P->devs[d].seg_begin >= 0) CU(cudaStreamWaitEvent(O->streams[0], P->devs[d].ev_chain, 0));
     }
 fail:
     return rc;

@@ -399,3 +399,58 @@ def test_one_shot_plan_cache(qh768, monkeypatch):
     assert sb.spMV_mgpu_v1(2000, 2000, len(v), 1.0, v, rp, c, x, 0.5, y, 1, 1) == 0
     check_tol(y, oracle.csr_spmv(rp, c, v, x, 1.0, 0.5, y0), oracle.csr_spmv_bound(rp, c, v, x, 1.0, 0.5, y0), "after clear")
     sb.cache_clear()
+
+
+def test_against_cusparse_generic_spmv(qh768):
+    """Third opinion on the arithmetic: the reference's csrmv is legacy cuSPARSE (removed in CUDA 11);
+    its living successor, the generic cusparseSpMV that torch's sparse CSR mat-vec calls, must agree
+    with this library (and with the oracle) to the same per-row bound.  Test-only use of a library."""
+    import torch
+    rng = np.random.default_rng(61)
+    lens = np.concatenate([rng.integers(0, 6, size=3000), rng.integers(100, 300, size=500), [20000, 0, 9000],
+                           np.full(5000, 2, np.int64), rng.integers(40, 120, size=5000)])
+    rp2, col2, val2 = make_csr(rng, len(lens), 7001, lens)
+    for rp, col, val, n in ((qh768["rowptr"], qh768["col"], qh768["val"], qh768["n"]), (rp2, col2, val2, 7001)):
+        m, nnz = len(rp) - 1, int(rp[-1])
+        x, y0 = rng.uniform(0.5, 1.5, n), rng.standard_normal(m)
+        A_t = torch.sparse_csr_tensor(torch.from_numpy(rp), torch.from_numpy(col.astype(np.int64)), torch.from_numpy(val),
+                                      size=(m, n), dtype=torch.float64, device="cuda")
+        ax = (A_t @ torch.from_numpy(x).cuda()).cpu().numpy()
+        lib_y = y0.copy()
+        assert sb.spMV_mgpu_v1(m, n, nnz, A, val, rp, col, x, B, lib_y, 1, 1) == 0, sb.last_error()
+        bound = oracle.csr_spmv_bound(rp, col, val, x, A, B, y0)
+        check_tol(lib_y, A * ax + B * y0, 2.0 * bound, "vs cusparse generic SpMV")
+        check_tol(A * ax + B * y0, oracle.csr_spmv(rp, col, val, x, A, B, y0), 2.0 * bound, "cusparse vs oracle")
+
+
+def test_chained_products_stay_on_the_devices():
+    """Iterative use: y -> x on every GPU with sblas_spmv_plan_chain (NVLink
+    all-gather of the owned row slices, no host copy), then the next product.  Every product is
+    checked against the oracle applied to the previous result; the gathered x is bit-identical to
+    the y that was downloaded."""
+    rng = np.random.default_rng(71)
+    lens = np.concatenate([rng.integers(1, 9, size=3000), [40000, 3, 25000], rng.integers(60, 200, size=800)])
+    m = len(lens)
+    rp, col, val = make_csr(rng, m, m, lens)
+    val *= 0.05
+    nnz = int(rp[-1])
+    for g in gpu_counts():
+        for version, nb, q in ((sb.V1, 0, 1), (sb.V2, nnz // (3 * g) + 1, 2)):
+            p = sb.Plan.create(version, m, m, nnz, val, rp, col, g, kernel=1, nb=nb, q=q)
+            x = rng.uniform(0.5, 1.5, m)
+            y = np.zeros(m)
+            p.upload(x, None)
+            for it in range(4):
+                p.execute_device(1.25, 0.0, sync=False)
+                y_dev = np.zeros(m)
+                p.download(y_dev)
+                want = oracle.csr_spmv(rp, col, val, x, 1.25, 0.0, y)
+                check_tol(y_dev, want, oracle.csr_spmv_bound(rp, col, val, x, 1.25, 0.0, y), "chain it %d g %d" % (it, g))
+                p.chain()
+                sb.device_synchronize()
+                for d in range(p.num_devices):
+                    xd = np.zeros(m)
+                    sb.memcpy(xd, p.x_ptr(d), 8 * m, 2)
+                    assert (xd == y_dev).all(), (it, g, d)
+                x = y_dev
+            p.destroy()
