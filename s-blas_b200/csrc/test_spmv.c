@@ -316,6 +316,19 @@ loaded:;
             const double bytes = sblas_spmv_plan_alg_bytes(plan, BETA != 0.0, -1);
             printf("[sblas] resident plan (v1, %d GPU): %.6f s/SpMV  %.1f GFLOP/s  %.1f GB/s algorithmic (%.1f%% of %d x 8000 GB/s)\n",
                    ngpu, t, flop / t / 1e9, bytes / t / 1e9, 100.0 * bytes / t / 1e9 / (8000.0 * ngpu), ngpu);
+            if (m == n) {
+                /* chained products x <- y (device-side NVLink all-gather between products, beta = 0 so
+                 * that the iterates stay bounded only by the matrix; timing only) */
+                const double t1 = get_time();
+                for (int i = 0; i < reps; i++) {
+                    sblas_spmv_plan_execute_device(plan, ALPHA, 0.0, 0);
+                    sblas_spmv_plan_chain(plan);
+                }
+                sblas_spmv_plan_execute_device(plan, ALPHA, 0.0, 1);
+                const double tc = (get_time() - t1) / (reps + 1);
+                printf("[sblas] chained (x <- y on the GPUs, %d GPU): %.6f s/SpMV  %.1f GFLOP/s  (all-gather of %.1f MB per GPU per product)\n",
+                       ngpu, tc, flop / tc / 1e9, 8.0 * m / 1e6);
+            }
             sblas_spmv_plan_destroy(plan);
         }
     }
