@@ -100,7 +100,9 @@ int sblas_spmv_plan_create(sblas_spmv_plan **plan, int version, int m, int n, lo
  * pointers to the WHOLE matrix unless SBLAS_SRC_DEVICE_SHARD is set in `flags`,
  * in which case csrVal/csrColIndex are DEVICE pointers to exactly this rank's
  * nnz range [start_idx, end_idx] (adopted, not copied) and csrRowPtr is still
- * the whole host row pointer. */
+ * the whole host row pointer.  Adopted arrays must start on a 32-byte boundary and
+ * be readable for 16 bytes past their last entry (the kernels fetch them with
+ * 16-byte-granular bulk copies; any cudaMalloc / framework allocation qualifies). */
 enum { SBLAS_SRC_HOST = 0, SBLAS_SRC_DEVICE_SHARD = 1, SBLAS_LAYOUT_ONLY = 2 };
 int sblas_spmv_plan_create_rank(sblas_spmv_plan **plan, int version, int m, int n, long long nnz,
                                 const double *csrVal, const long long *csrRowPtr, const int *csrColIndex,
