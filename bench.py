@@ -468,7 +468,11 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
-    h2d = 8 * n * world + 8 * m          # every rank uploads x; y slices add up to m (+ shared rows)
+    xw = plan.x_window()                  # every rank uploads the window of x its shard references
+    xb = torch.tensor([8.0 * (xw[1] - xw[0] + 1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(xb, op=dist.ReduceOp.SUM)
+    h2d = int(xb.item()) + 8 * m         # + the y slices, which add up to m (+ shared rows)
     d2h = 8 * m
 
     if rank == 0:

@@ -71,6 +71,10 @@ cudaError_t sblas_launch_tile_meta(const sblas_seg_args *a, int tile, int *tmeta
 cudaError_t sblas_launch_row_block_stats(const int *rowptr, int row_lo, int nrows, int rb, int nz0, int nz1,
                                          int *out_max, int *out_ptr, cudaStream_t s);
 
+/* out_min_max[0] = min(out[0], min col), out_min_max[1] = max(out[1], max col) over col[0..count):
+ * the window of x a shard can read (initialise to {INT_MAX, -1}). */
+cudaError_t sblas_launch_col_range(const int *col, long long count, int *out_min_max, cudaStream_t s);
+
 /* y[row_lo..row_hi] = alpha*A_seg*x + beta*y for one segment. kind: SBLAS_K_*;
  * ipt: items per thread of the tile kernel (4, 8 or 16); lanes: lanes per row of
  * the vector kernel (0 = choose from the mean row length). */

@@ -136,7 +136,11 @@ int sblas_spmv_plan_execute_device(sblas_spmv_plan *plan, double alpha, double b
 int sblas_spmv_plan_num_devices(const sblas_spmv_plan *plan);
 int sblas_spmv_plan_num_segments(const sblas_spmv_plan *plan);
 int sblas_spmv_plan_segment(const sblas_spmv_plan *plan, int seg, sblas_part *out, int *device);
-double *sblas_spmv_plan_x(sblas_spmv_plan *plan, int dev);            /* device pointer, n doubles      */
+double *sblas_spmv_plan_x(sblas_spmv_plan *plan, int dev);
+/* the columns the GPU's resident shard references, [first_col, last_col]: a plan with one GPU in
+ * this process uploads only that window of x (the reference uploads all of x to every GPU,
+ * dspmv_mgpu_v1.cu:183) */
+int sblas_spmv_plan_x_window(const sblas_spmv_plan *plan, int dev, long long *first_col, long long *last_col);            /* device pointer, n doubles      */
 double *sblas_spmv_plan_y(sblas_spmv_plan *plan, int dev, int *first_row, int *rows); /* device y slice */
 const int *sblas_spmv_plan_rowptr(sblas_spmv_plan *plan, int dev, int *count);        /* device int32   */
 void *sblas_spmv_plan_stream(sblas_spmv_plan *plan, int dev);         /* cudaStream_t of the GPU        */

@@ -112,6 +112,7 @@ def lib():
     L.sblas_spmv_plan_alg_bytes.restype = C.c_double
     L.sblas_spmv_plan_launches.argtypes = [_vp]
     L.sblas_spmv_plan_num_units.argtypes = [_vp]
+    L.sblas_spmv_plan_x_window.argtypes = [_vp, C.c_int, P(_LL), P(_LL)]
     L.sblas_spmv_plan_chain.argtypes = [_vp]
     L.sblas_mtx_info.argtypes = [C.c_char_p, P(C.c_int), P(C.c_int), P(_LL), P(C.c_int)]
     L.sblas_mtx_read_csr.argtypes = [C.c_char_p, _vp, _vp, _vp]
@@ -300,6 +301,12 @@ class Plan:
         rc = lib().sblas_spmv_plan_execute_device(self._h, alpha, beta, 1 if sync else 0)
         if rc != 0:
             raise RuntimeError("sblas_spmv_plan_execute_device rc=%d: %s" % (rc, last_error()))
+
+    def x_window(self, dev=0):
+        """[first, last] column the GPU's shard references (what upload() copies of x)."""
+        a, b = _LL(), _LL()
+        assert lib().sblas_spmv_plan_x_window(self._h, dev, C.byref(a), C.byref(b)) == 0
+        return int(a.value), int(b.value)
 
     def chain(self):
         """x <- y on every GPU of the plan (device-side all-gather over NVLink); then execute_device."""

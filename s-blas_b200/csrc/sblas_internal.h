@@ -41,6 +41,7 @@ typedef struct sblas_dev {
     cudaEvent_t ev_y, ev_chain;       /* y complete on this GPU / this GPU has pulled every y slice (chain) */
     int kind, ipt;
     long long xs_lo, xs_hi;           /* slice of x this GPU uploads itself */
+    int col_lo, col_hi;               /* smallest / largest column of the resident shard: the x it reads */
 } sblas_dev;
 
 struct sblas_spmv_plan {

@@ -472,6 +472,26 @@ __global__ void row_block_stats_kernel(const int *__restrict__ rowptr, int row_l
     }
 }
 
+/* smallest and largest column index of a shard: the only part of x its products can read */
+__global__ void col_range_kernel(const int *__restrict__ col, long long count, int *__restrict__ out)
+{
+    int lo = 0x7fffffff, hi = -1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        const int c = __ldg(col + i);
+        lo = min(lo, c);
+        hi = max(hi, c);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        lo = min(lo, __shfl_xor_sync(kFull, lo, off));
+        hi = max(hi, __shfl_xor_sync(kFull, hi, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(out, lo);
+        atomicMax(out + 1, hi);
+    }
+}
+
 __global__ void rebase_rowptr_kernel(const long long *__restrict__ rp64, long long first_idx, int total,
                                      long long count, int *__restrict__ out)
 {
@@ -651,6 +671,15 @@ extern "C" cudaError_t sblas_launch_row_block_stats(const int *rowptr, int row_l
     const int nb = (nrows + rb - 1) / rb;
     if (nb <= 0) return cudaSuccess;
     row_block_stats_kernel<<<nb, kThreads, 0, s>>>(rowptr, row_lo, nrows, rb, nz0, nz1, out_max, out_ptr);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t sblas_launch_col_range(const int *col, long long count, int *out_min_max, cudaStream_t s)
+{
+    if (count <= 0) return cudaSuccess;
+    long long blocks = (count + 4095) / 4096;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    col_range_kernel<<<(unsigned)blocks, 256, 0, s>>>(col, count, out_min_max);
     return cudaGetLastError();
 }
 

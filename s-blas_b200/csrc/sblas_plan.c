@@ -407,6 +407,19 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
         CU(cudaStreamSynchronize(st));
         CU(cudaFree(stage64)); stage64 = NULL;
 
+        /* the window of x this shard reads: [col_lo, col_hi] (one reduction over col at plan time) */
+        D->col_lo = 0; D->col_hi = P->n - 1;
+        if (D->nnz > 0 && env_int("SBLAS_X_WINDOW", 1)) {
+            int *d_mm = NULL, h_mm[2] = {0x7fffffff, -1};
+            CU(cudaMalloc((void **)&d_mm, 2 * sizeof(int)));
+            CU(cudaMemcpyAsync(d_mm, h_mm, sizeof h_mm, cudaMemcpyHostToDevice, st));
+            CU(sblas_launch_col_range(D->d_col, D->nnz, d_mm, st));
+            CU(cudaMemcpyAsync(h_mm, d_mm, sizeof h_mm, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            cudaFree(d_mm);
+            if (h_mm[0] >= 0 && h_mm[1] < P->n && h_mm[0] <= h_mm[1]) { D->col_lo = h_mm[0]; D->col_hi = h_mm[1]; }
+        }
+
         /* edge table: 2 doubles per local segment, device memory (peers read it over NVLink) */
         const int nl = D->seg_end - D->seg_begin;
         CU(cudaMalloc((void **)&D->d_edge, (size_t)(2 * (P->rank_mode ? P->max_local : nl) + 2) * sizeof(double)));
@@ -807,7 +820,8 @@ int sblas_spmv_plan_upload(sblas_spmv_plan *P, const double *x, const double *y)
         if (D->seg_begin < 0) continue;
         CU(cudaSetDevice(D->device));
         cudaStream_t st = D->streams[0];
-        const long long lo = (long long)P->n * li / live, hi = (long long)P->n * (li + 1) / live;
+        long long lo = (long long)P->n * li / live, hi = (long long)P->n * (li + 1) / live;
+        if (live == 1) { lo = D->col_lo; hi = (long long)D->col_hi + 1; }     /* only what the shard reads */
         D->xs_lo = lo; D->xs_hi = hi;
         if (x && hi > lo)
             CU(cudaMemcpyAsync(D->d_x + lo, x + lo, (size_t)(hi - lo) * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -973,6 +987,13 @@ int sblas_spmv_plan_segment(const sblas_spmv_plan *P, int seg, sblas_part *out, 
     return 0;
 }
 double *sblas_spmv_plan_x(sblas_spmv_plan *P, int dev) { return P->devs[dev].d_x; }
+int sblas_spmv_plan_x_window(const sblas_spmv_plan *P, int dev, long long *first_col, long long *last_col)
+{
+    if (dev < 0 || dev >= P->ndev) return -1;
+    if (first_col) *first_col = P->devs[dev].col_lo;
+    if (last_col) *last_col = P->devs[dev].col_hi;
+    return 0;
+}
 double *sblas_spmv_plan_y(sblas_spmv_plan *P, int dev, int *first_row, int *rows)
 {
     if (first_row) *first_row = P->devs[dev].first_row;

@@ -454,3 +454,25 @@ def test_chained_products_stay_on_the_devices():
                     assert (xd == y_dev).all(), (it, g, d)
                 x = y_dev
             p.destroy()
+
+
+def test_upload_moves_only_the_columns_a_shard_reads():
+    """A one-GPU (or one-rank) plan copies x[first_col..last_col] of its shard only; stale x outside the
+    window must not matter, and the window is exact."""
+    rng = np.random.default_rng(83)
+    m, n = 3000, 50000
+    lens = rng.integers(1, 40, size=m)
+    rp = np.zeros(m + 1, np.int64)
+    np.cumsum(lens, out=rp[1:])
+    nnz = int(rp[-1])
+    col = rng.integers(12345, 23456, size=nnz, dtype=np.int64).astype(np.int32)
+    col[7], col[nnz // 2] = 12000, 23999
+    val = rng.uniform(-1, 1, size=nnz)
+    p = sb.Plan.create(sb.V1, m, n, nnz, val, rp, col, 1, kernel=1)
+    assert p.x_window() == (12000, 23999)
+    for it in range(2):
+        x, y0 = rng.standard_normal(n), rng.standard_normal(m)
+        y = y0.copy()
+        p.execute(A, x, B, y)
+        check_tol(y, oracle.csr_spmv(rp, col, val, x, A, B, y0), oracle.csr_spmv_bound(rp, col, val, x, A, B, y0), "x window %d" % it)
+    p.destroy()
