@@ -452,6 +452,9 @@ def main():
     xh_np, yh_np = xh_p.numpy(), yh_p.numpy()
 
     def e2e_step():
+        if world == 1:                     # the plan's host API: one call, host x and y in, host y out
+            plan.execute(ALPHA, xh_np, BETA, yh_np)
+            return
         plan.upload(xh_np, yh_np)
         with torch.cuda.stream(stream):
             step()
@@ -515,7 +518,9 @@ def main():
                                                     "nnz": u["nz1"] - u["nz0"]} for u in units]}},
             "e2e": {"value": 2.0 * nnz / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
-                    "api": "sblas_spmv_plan_upload + execute_device (+ edge all-gather/merge) + download on a resident plan"},
+                    "api": ("sblas_spmv_plan_execute on a resident plan (host x, y in; host y out; y slices of the row panels "
+                            "move while other panels compute)") if world == 1 else
+                           "sblas_spmv_plan_upload + execute_device + fused split-row exchange + download on a resident plan"},
             "gpu_launches": args.steps * (plan.launches + (2 if exchange == "symm" else 1 if exchange == "nccl" else 0)),
             "clocks": clocks, "parity_check": check,
         }

@@ -38,6 +38,8 @@ typedef struct sblas_dev {
     int *h_mrow, *h_mbeg; const double **h_msrc; long long *h_msrc_off;
     cudaStream_t *streams; int nstreams;
     cudaEvent_t *ev_seg, ev_in, ev_done;
+    cudaStream_t copy_stream;         /* second stream: y slices move while other panels compute */
+    cudaEvent_t *ev_unit; int nev_unit; /* per panel: its y slice is on the GPU / its kernel is done */
     cudaEvent_t ev_y, ev_chain;       /* y complete on this GPU / this GPU has pulled every y slice (chain) */
     int kind, ipt;
     long long xs_lo, xs_hi;           /* slice of x this GPU uploads itself */

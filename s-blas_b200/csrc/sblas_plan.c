@@ -120,6 +120,9 @@ static void free_dev(sblas_dev *D, int dry)
     }
     if (D->ev_in) cudaEventDestroy(D->ev_in);
     if (D->ev_done) cudaEventDestroy(D->ev_done);
+    if (D->copy_stream) cudaStreamDestroy(D->copy_stream);
+    for (int i = 0; i < D->nev_unit; ++i) if (D->ev_unit[i]) cudaEventDestroy(D->ev_unit[i]);
+    free(D->ev_unit);
     if (D->ev_y) cudaEventDestroy(D->ev_y);
     if (D->ev_chain) cudaEventDestroy(D->ev_chain);
     free(D->streams); free(D->ev_seg);
@@ -938,9 +941,72 @@ fail:
     return rc;
 }
 
+/* One GPU, one segment, several row panels: the y slice of panel u+1 goes up and the finished
+ * slice of panel u-1 comes down on a second stream while panel u computes; only the first panel's
+ * upload and the last panel's download are exposed. */
+static int execute_pipelined(sblas_spmv_plan *P, double alpha, const double *x, double beta, double *y)
+{
+    int rc = 0;
+    sblas_dev *D = &P->devs[0];
+    sblas_seg *S = &P->segs[D->seg_begin];
+    const int nu = S->unit_end - S->unit_begin;
+    CU(cudaSetDevice(D->device));
+    if (!D->copy_stream) CU(cudaStreamCreateWithFlags(&D->copy_stream, cudaStreamNonBlocking));
+    if (D->nev_unit < 2 * nu) {
+        cudaEvent_t *ev = (cudaEvent_t *)calloc((size_t)2 * nu, sizeof(cudaEvent_t));
+        if (!ev) return 1;
+        for (int i = 0; i < D->nev_unit; ++i) ev[i] = D->ev_unit[i];
+        free(D->ev_unit);
+        D->ev_unit = ev;
+        for (int i = D->nev_unit; i < 2 * nu; ++i) CU(cudaEventCreateWithFlags(&D->ev_unit[i], cudaEventDisableTiming));
+        D->nev_unit = 2 * nu;
+    }
+    cudaStream_t st = D->streams[0], cs = D->copy_stream;
+    if (x && D->col_hi >= D->col_lo)
+        CU(cudaMemcpyAsync(D->d_x + D->col_lo, x + D->col_lo, (size_t)(D->col_hi - D->col_lo + 1) * sizeof(double),
+                           cudaMemcpyHostToDevice, st));
+    /* uploads: panel 0 on the compute stream, the others on the copy stream */
+    for (int u = 0; u < nu && beta != 0.0; ++u) {
+        const sblas_seg_args *a = &P->units[S->unit_begin + u].args;
+        const long long rows = (long long)a->row_hi - a->row_lo + 1;
+        if (rows <= 0) continue;
+        CU(cudaMemcpyAsync(D->d_y + a->row_lo, y + D->first_row + a->row_lo, (size_t)rows * sizeof(double),
+                           cudaMemcpyHostToDevice, u == 0 ? st : cs));
+        if (u > 0) CU(cudaEventRecord(D->ev_unit[2 * u], cs));
+    }
+    for (int u = 0; u < nu; ++u) {
+        sblas_unit *U = &P->units[S->unit_begin + u];
+        const sblas_seg_args *a = &U->args;
+        const long long rows = (long long)a->row_hi - a->row_lo + 1;
+        if (u > 0 && beta != 0.0 && rows > 0) CU(cudaStreamWaitEvent(st, D->ev_unit[2 * u], 0));
+        U->args.alpha = alpha; U->args.beta = beta;
+        U->args.edge = S->args.edge;
+        CU(sblas_launch_spmv_segment(&U->args, U->kind, U->ipt, 0, st));
+        if (rows <= 0) continue;
+        if (u + 1 < nu) {                          /* comes down while the next panel computes */
+            CU(cudaEventRecord(D->ev_unit[2 * u + 1], st));
+            CU(cudaStreamWaitEvent(cs, D->ev_unit[2 * u + 1], 0));
+            CU(cudaMemcpyAsync(y + D->first_row + a->row_lo, D->d_y + a->row_lo, (size_t)rows * sizeof(double),
+                               cudaMemcpyDeviceToHost, cs));
+        } else {
+            CU(cudaMemcpyAsync(y + D->first_row + a->row_lo, D->d_y + a->row_lo, (size_t)rows * sizeof(double),
+                               cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CU(cudaEventRecord(D->ev_done, st));
+    CU(cudaStreamSynchronize(cs));
+    CU(cudaStreamSynchronize(st));
+fail:
+    return rc;
+}
+
 int sblas_spmv_plan_execute(sblas_spmv_plan *P, const double *alpha, const double *x, const double *beta, double *y)
 {
     int rc;
+    if (!P->dry && P->ndev == 1 && P->nseg == 1 && P->devs[0].seg_begin >= 0 && P->devs[0].nmerge == 0 &&
+        P->devs[0].nstreams == 1 && (!P->rank_mode || P->world == 1) && x && y &&
+        P->segs[0].unit_end - P->segs[0].unit_begin >= 2 && env_int("SBLAS_PIPELINE", 1))
+        return execute_pipelined(P, *alpha, x, *beta, y);
     if ((rc = sblas_spmv_plan_upload(P, x, *beta != 0.0 ? y : NULL)) != 0) return rc;
     if ((rc = sblas_spmv_plan_execute_device(P, *alpha, *beta, 0)) != 0) return rc;
     return sblas_spmv_plan_download(P, y);
