@@ -210,7 +210,7 @@ class ClockSampler:
             for ts, ln in self.lines:
                 f = [c.strip() for c in ln.split(",")]
                 try:
-                    if ts >= t0 - 2.0:
+                    if ts >= t0 - 3.0:
                         sm.append(float(f[1]))
                 except (ValueError, IndexError):
                     pass
@@ -379,11 +379,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi needs a moment
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
             step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler is not None and sampler.p is not None and world == 1:
+        t_w = time.time()                                      # keep the GPU busy until the first sample arrives
+        while not sampler.lines and time.time() - t_w < 3.0:
+            with torch.cuda.stream(stream):
+                step()
+            torch.cuda.synchronize()
+    barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     t_wall0 = time.time()
     with torch.cuda.stream(stream):
