@@ -380,6 +380,10 @@ def main():
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi needs a moment
+    if sampler is not None and sampler.p is not None and world > 1:
+        t_w = time.time()                                      # the other ranks wait at the barrier below
+        while not sampler.lines and time.time() - t_w < 3.0:
+            time.sleep(0.05)
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
             step()
