@@ -197,6 +197,12 @@ int sblas_spmv_plan_launches(const sblas_spmv_plan *plan);
  * out = {local segment, kernel kind (SBLAS_K_*), ipt / R | window << 8, first row, last row
  *        (global, inclusive), first entry, one-past-last entry (global), launches}. */
 int sblas_spmv_plan_num_units(const sblas_spmv_plan *plan);
+/* The row-binning rule on host arrays (no CUDA): block b of 4096 rows has longest row
+ * block_longest[b] and starts at entry block_first_entry[b]; outputs one (class, R, first block)
+ * per run, class 0 general / 1 short / 2 medium, run_begin[nruns] = nblocks; returns nruns.
+ * All output arrays need nblocks + 2 ints. */
+int sblas_bin_row_blocks(const int *block_longest, const int *block_first_entry, int nblocks, int nrows, int nz_end,
+                         int short_max, int medium_on, long long min_nnz, int *run_class, int *run_R, int *run_begin);
 int sblas_spmv_plan_unit(const sblas_spmv_plan *plan, int i, long long out[8]);
 /* launch ONE panel's kernel(s) on its stream (measurement: time a kernel alone) */
 int sblas_spmv_plan_execute_unit(sblas_spmv_plan *plan, int i, double alpha, double beta);

@@ -289,6 +289,16 @@ static int bin_blocks(const int *bmax, const int *bptr, int nblk, int nrows, int
     return w;
 }
 
+/* the binning rule alone, on host arrays (tests and tools; no CUDA): see bin_blocks */
+int sblas_bin_row_blocks(const int *block_longest, const int *block_first_entry, int nblocks, int nrows, int nz_end,
+                         int short_max, int medium_on, long long min_nnz, int *run_class, int *run_R, int *run_begin)
+{
+    const int n = bin_blocks(block_longest, block_first_entry, nblocks, nrows, nz_end, short_max, medium_on, min_nnz,
+                             run_class, run_R, run_begin);
+    for (int i = 0; i < n; ++i) if (run_class[i] == 2) run_R[i] &= 0xff; else run_R[i] = 0;
+    return n;
+}
+
 static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp, const int *col,
                       const int *devices, int src_flags)
 {
