@@ -95,6 +95,10 @@ def workload(name):
         m = 6_250_000
         return dict(m=m, n=1_000_000, row_len=two_block(m, m, 180, 180), cols_mode=sb.COLS_PREFIX, band=0,
                     desc="diagnostic: 6.25M rows x 180 nnz, prefix columns")
+    if name == "rows1000":     # diagnostic: the short-row block of g100000 alone (x12 rows)
+        m = 1_050_000
+        return dict(m=m, n=1_000_000, row_len=two_block(m, m, 1000, 1000), cols_mode=sb.COLS_PREFIX, band=0,
+                    desc="diagnostic: 1.05M rows x 1,000 nnz, prefix columns")
     if name == "rows2":        # diagnostic: the short-row block of big50m alone
         m = 43_750_000
         return dict(m=m, n=50_000_000, row_len=two_block(m, m, 2, 2), cols_mode=sb.COLS_BANDRUN, band=1 << 20,

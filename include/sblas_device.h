@@ -43,7 +43,8 @@ typedef struct sblas_seg_args {
 /* kernel families (the `kernel` argument of the reference API maps onto these,
  * see sblas_plan.c) */
 enum { SBLAS_K_VECTOR = 1, SBLAS_K_TILE = 2, SBLAS_K_TMA = 3, SBLAS_K_VECP = 4, SBLAS_K_SHORT = 5,
-       SBLAS_K_ROWTILE = 6 /* ipt = R | window << 8: R rows per warp, every R consecutive rows hold <= window <= 256 entries */ };
+       SBLAS_K_ROWTILE = 6 /* ipt = R | window << 8: R rows per warp, every R consecutive rows hold <= window <= 256 entries */,
+       SBLAS_K_ROWSPLIT = 7 /* ipt = G (2, 4, 8) warps per row: every row of the panel holds <= 256*G entries */ };
 
 /* nnz per tile of the tile kernel for a given items-per-thread choice (kind TILE),
  * or of the TMA-pipelined kernel (kind TMA, ipt ignored) */

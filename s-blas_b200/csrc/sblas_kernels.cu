@@ -27,7 +27,8 @@
 
 cudaError_t sblas_launch_tma(const sblas_seg_args *a, cudaStream_t s);      /* sblas_spmv_tma.cu */
 int sblas_tma_tile_size(void);
-cudaError_t sblas_launch_rowtile(const sblas_seg_args *a, int R, int window, cudaStream_t s);  /* sblas_spmv_rowtile.cu */
+cudaError_t sblas_launch_rowtile(const sblas_seg_args *a, int R, int window, cudaStream_t s);
+cudaError_t sblas_launch_rowsplit(const sblas_seg_args *a, int G, cudaStream_t s);  /* sblas_spmv_rowtile.cu */
 
 namespace {
 
@@ -731,6 +732,7 @@ extern "C" cudaError_t sblas_launch_spmv_segment(const sblas_seg_args *a, int ki
     const long long nnz = (long long)a->nz1 - a->nz0;
     if (kind == SBLAS_K_VECP) return ipt == 4 ? launch_vecp<4>(a, s) : launch_vecp<8>(a, s);
     if (kind == SBLAS_K_ROWTILE) return sblas_launch_rowtile(a, ipt & 0xff, ipt >> 8, s);
+    if (kind == SBLAS_K_ROWSPLIT) return sblas_launch_rowsplit(a, ipt, s);
     if (kind == SBLAS_K_SHORT) {
         spmv_short_kernel<<<(unsigned)((nrows + kThreads * kShortRows - 1) / (kThreads * kShortRows)), kThreads, 0, s>>>(*a);
         return cudaGetLastError();

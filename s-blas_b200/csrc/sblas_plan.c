@@ -238,6 +238,9 @@ static sblas_unit *new_unit(sblas_spmv_plan *P)
  *   class 1 "short"   every row holds at most `short_max` entries -> thread-per-row kernel
  *   class 2 "medium"  longest row in [16, 256] and the rows fill at least half of a warp's
  *                     256-entry window -> warp per R = floor(256/longest) whole rows (row-tile kernel)
+ *   class 3 "long-medium"  longest row in (256, 2048] and the mean row at least half of the 256*G
+ *                     entries G = 2, 4 or 8 warps cover -> G warps per row (row-split kernel); off
+ *                     unless `medium_on` has bit 1 set
  *   class 0 "general" everything else -> the GPU's general kernel (the nnz-balanced TMA tile
  *                     kernel, whose per-tile reduction adapts further)
  * Runs below `min_nnz` entries are not worth a launch of their own and turn general; equal
@@ -264,10 +267,14 @@ static int bin_blocks(const int *bmax, const int *bptr, int nblk, int nrows, int
             R = 256 / bmax[b];
             if (R > 8) R = 8;
             if (bn * R >= 128 * br) cls = 2;
+        } else if ((medium_on & 2) && bmax[b] > 256 && bmax[b] <= 2048) {
+            R = bmax[b] <= 512 ? 2 : bmax[b] <= 1024 ? 4 : 8;           /* G warps per row */
+            if (bn >= 128LL * R * br) cls = 3;
         }
         if (cls == 2) R |= bmax[b] << 8;                     /* R | longest row << 8 */
         if (nrun > 0 && run_class[nrun - 1] == cls) {
             if (cls == 2) run_R[nrun - 1] = merge_R(run_R[nrun - 1], R);
+            if (cls == 3 && R > run_R[nrun - 1]) run_R[nrun - 1] = R;
             continue;
         }
         run_class[nrun] = cls; run_R[nrun] = R; run_begin[nrun] = b; ++nrun;
@@ -281,6 +288,7 @@ static int bin_blocks(const int *bmax, const int *bptr, int nblk, int nrows, int
     for (int i = 0; i < nrun; ++i) {
         if (w > 0 && run_class[w - 1] == run_class[i]) {
             if (run_class[i] == 2) run_R[w - 1] = merge_R(run_R[w - 1], run_R[i]);
+            if (run_class[i] == 3 && run_R[i] > run_R[w - 1]) run_R[w - 1] = run_R[i];
             continue;
         }
         run_class[w] = run_class[i]; run_R[w] = run_R[i]; run_begin[w] = run_begin[i]; ++w;
@@ -295,7 +303,7 @@ int sblas_bin_row_blocks(const int *block_longest, const int *block_first_entry,
 {
     const int n = bin_blocks(block_longest, block_first_entry, nblocks, nrows, nz_end, short_max, medium_on, min_nnz,
                              run_class, run_R, run_begin);
-    for (int i = 0; i < n; ++i) if (run_class[i] == 2) run_R[i] &= 0xff; else run_R[i] = 0;
+    for (int i = 0; i < n; ++i) if (run_class[i] == 2) run_R[i] &= 0xff; else if (run_class[i] != 3) run_R[i] = 0;
     return n;
 }
 
@@ -512,8 +520,10 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
                 sblas_unit *U = new_unit(P);
                 if (!U) { rc = 1; goto fail; }
                 U->args = *a;
-                U->kind = run_class[i] == 1 ? SBLAS_K_SHORT : run_class[i] == 2 ? SBLAS_K_ROWTILE : D->kind;
+                U->kind = run_class[i] == 1 ? SBLAS_K_SHORT : run_class[i] == 2 ? SBLAS_K_ROWTILE :
+                          run_class[i] == 3 ? SBLAS_K_ROWSPLIT : D->kind;
                 U->ipt = D->ipt;
+                if (run_class[i] == 3) U->ipt = run_R[i];          /* G warps per row */
                 if (run_class[i] == 2) {           /* R rows per warp, window = R x longest row (<= 256) */
                     const int R = run_R[i] & 0xff, win = R * (run_R[i] >> 8);
                     U->ipt = R | (win < 256 ? win : 256) << 8;

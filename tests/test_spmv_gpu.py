@@ -176,6 +176,36 @@ def test_row_tile_kernel_on_medium_panels(monkeypatch):
     run_all_versions(rp, col, val, x, -1.75, 0.625, y0, (1,), kernels=(1,), what="row tiles off")
 
 
+@pytest.mark.skipif(os.environ.get("SBLAS_TEST_ROWSPLIT") != "1",
+                    reason="experimental row-split kernel (SBLAS_MEDIUM bit 1, off by default); set SBLAS_TEST_ROWSPLIT=1 to run")
+def test_row_split_kernel_on_long_medium_panels(monkeypatch):
+    """Panels whose longest row lies in (256, 2048] and whose rows are mostly that long go to the row-split
+    kernel, G = 2 / 4 / 8 warps per row (SBLAS_MEDIUM bit 1).  One block per G, with empty and short rows
+    sprinkled in, split rows at shard/task borders (v1 x ngpu, v2 tasks)."""
+    monkeypatch.setenv("SBLAS_MEDIUM", "3")
+    monkeypatch.setenv("SBLAS_PANEL_MIN_NNZ", "2048")
+    monkeypatch.setenv("SBLAS_VEC_BELOW", "1")
+    rng = np.random.default_rng(91)
+    blocks = []
+    for longest in (512, 300, 1024, 700, 2048, 1500):
+        ln = rng.integers(longest // 2 + 1, longest + 1, size=4096)
+        ln[rng.integers(0, 4096, size=30)] = 0
+        ln[rng.integers(0, 4096, size=30)] = rng.integers(1, 40, size=30)
+        ln[rng.integers(0, 4096)] = longest
+        blocks.append(ln)
+    blocks.insert(2, np.full(5000, 2, np.int64))
+    blocks.append(np.array([30000, 1, 0, 700], np.int64))
+    lens = np.concatenate(blocks).astype(np.int64)
+    m, n = len(lens), 32749
+    rp, col, val = make_csr(rng, m, n, lens, sort_cols=False)
+    x, y0 = rng.standard_normal(n), rng.standard_normal(m)
+    p = sb.Plan.create(sb.V1, m, n, int(rp[-1]), val, rp, col, 1, kernel=1)
+    assert 7 in [u["kind"] for u in p.units()], p.units()
+    p.destroy()
+    run_all_versions(rp, col, val, x, -1.75, 0.625, y0, gpu_counts(), kernels=(1,), what="row split")
+    run_all_versions(rp, col, val, x, 2.0, 0.0, y0, (1,), kernels=(1,), what="row split beta=0")
+
+
 def test_row_spanning_many_segments():
     """A row longer than nnz/ngpu (v1) and than nb (v2): >= 3 segments share it."""
     rng = np.random.default_rng(17)
