@@ -247,3 +247,27 @@ def load_mtx_csr(path):
     rp = np.zeros(m + 1, np.int64)
     np.cumsum(np.bincount(rows, minlength=m), out=rp[1:])
     return m, n, rp, np.asarray(cols, np.int32)[order], np.asarray(vals, np.float64)[order], sym
+
+
+def ref_ingest():
+    """The reference's OWN correct loader (mmio_highlevel.h) compiled by oracle/Makefile, or None."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libref_ingest.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.ref_mmio_info.argtypes = [C.POINTER(C.c_int)] * 4 + [C.c_char_p]
+    L.ref_mmio_data.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p]
+
+    def load(p):
+        m, n, nnz, sym = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        rc = L.ref_mmio_info(C.byref(m), C.byref(n), C.byref(nnz), C.byref(sym), p.encode())
+        if rc != 0:
+            raise IOError("ref mmio_info rc=%d" % rc)
+        rp = np.zeros(m.value + 1, np.int32)
+        col = np.zeros(max(nnz.value, 1), np.int32)
+        val = np.zeros(max(nnz.value, 1), np.float64)
+        rc = L.ref_mmio_data(rp.ctypes.data, col.ctypes.data, val.ctypes.data, p.encode())
+        if rc != 0:
+            raise IOError("ref mmio_data rc=%d" % rc)
+        return m.value, n.value, rp.astype(np.int64), col[:nnz.value], val[:nnz.value], bool(sym.value)
+    return load

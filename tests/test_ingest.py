@@ -105,3 +105,46 @@ def test_sample_matrix_through_the_correct_loader():
     m, n, rp, col, val, sym = sb.mtx_read_csr(path)
     assert (m, n, int(rp[-1]), sym) == (768, 768, 2934, False)
     assert np.array_equal(dense(m, n, rp, col, val), scipy.io.mmread(path).toarray())
+
+
+GOLDEN_CASES = ["real_general", "real_symmetric", "pattern_general", "pattern_symmetric", "integer_general",
+                "integer_symmetric", "complex_hermitian"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_ingest_matches_the_reference_loader_golden(name):
+    """Pinned: the CSR arrays the REFERENCE's own loader (mmio_highlevel.h, compiled by oracle/Makefile)
+    produced for the committed fixtures (tests/golden/make_golden_ingest.py) -- entry for entry, for the
+    product and for the oracle restatement."""
+    g = np.load(os.path.join(GOLDEN, "ingest_expected.npz"))
+    path = os.path.join(GOLDEN, "ingest_%s.mtx" % name)
+    for loader in (sb.mtx_read_csr, oracle.load_mtx_csr):
+        m, n, rp, col, val, sym = loader(path)
+        assert [m, n, int(sym)] == g[name + "_mn"].tolist()
+        assert (rp == g[name + "_rowptr"]).all() and (col == g[name + "_col"]).all() and (val == g[name + "_val"]).all()
+
+
+def test_ingest_matches_the_compiled_reference_loader_live(tmp_path):
+    """Same comparison against the reference loader itself when oracle/_ref/libref_ingest.so is present
+    (it travels with the repo snapshot), on fresh random files."""
+    ref = oracle.ref_ingest()
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_ingest.so not built (needs the reference checkout at build time)")
+    for k, (field, symm) in enumerate(CASES):
+        rng = np.random.default_rng(500 + k)
+        m, n = 61, 47 if symm == "general" else 61
+        ents = {}
+        for _ in range(500):
+            i, j = int(rng.integers(0, m)), int(rng.integers(0, n))
+            if symm != "general" and j > i:
+                i, j = j, i
+            ents[(i, j)] = float(rng.integers(-9, 10)) if field == "integer" else float(rng.standard_normal())
+        entries = [(i, j, v) for (i, j), v in ents.items()]
+        rng.shuffle(entries)
+        path = str(tmp_path / ("r%d.mtx" % k))
+        write_mtx(path, m, n, entries, field, symm)
+        want = ref(path)
+        for loader in (sb.mtx_read_csr, oracle.load_mtx_csr):
+            got = loader(path)
+            assert got[0:2] == want[0:2] and got[5] == want[5]
+            assert (got[2] == want[2]).all() and (got[3] == want[3]).all() and (got[4] == want[4]).all()
