@@ -76,6 +76,19 @@ __device__ __forceinline__ uint64_t policy_evict_first()
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+/* Hand a stage back to the producer only once the values read from it have ARRIVED in registers.
+ * `witness` is the result of arithmetic on every value the warp loaded from the stage; making the
+ * arrive conditional on it gives nvcc and ptxas a true dependency, so the arrive cannot be
+ * scheduled while one of those shared-memory loads is still in flight.  (It was, in SASS: arrive
+ * issued between the last LDS and the FMA that consumes it.  With scattered x gathers the LSU queue
+ * gets deep enough for such a load to return AFTER the next bulk copy has rewritten the stage --
+ * seen as one wrong part in ~1e-3 of the long rows of a test matrix.)  The condition is always
+ * true: a computed double is never a signalling NaN, and 0x7ff0dead is one. */
+__device__ __forceinline__ void release_after(uint32_t empty_bar, int lane, double witness)
+{
+    __syncwarp();
+    if (lane == 0 && __double2hiint(witness) != 0x7ff0dead) mbar_arrive(empty_bar);
+}
 __device__ __forceinline__ void fence_proxy_async_smem()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -194,8 +194,13 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas
             const int pos = ccb + 32 * i + lane;
             p[i] = (pos < cce) ? S.val[pos] * xv[i] : 0.0;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty0 + 8u * s);
+        double psum = p[0], psum1 = p[1];                  /* every product: the witness of the release, and */
+#pragma unroll
+        for (int i = 2; i < NS; i += 2) psum += p[i];      /* the row sum itself when R == 1               */
+#pragma unroll
+        for (int i = 3; i < NS; i += 2) psum1 += p[i];
+        psum += psum1;
+        release_after(empty0 + 8u * s, lane, psum);        /* the stage goes back once its values are in registers */
 
         /* lane 4c owns row cfirst + c (R == 1: lane 0) */
         const int pc = lane >> 2;
@@ -211,12 +216,7 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas
         /* (3) row sums */
         double mine;
         if (R == 1) {
-            double t = p[0], t1 = p[1];
-#pragma unroll
-            for (int i = 2; i < NS; i += 2) t += p[i];
-#pragma unroll
-            for (int i = 3; i < NS; i += 2) t1 += p[i];
-            mine = warp_sum(t + t1);
+            mine = warp_sum(psum);
         } else if (R == 2) {
             /* two rows: two accumulators split at the second row's start, two interleaved reductions */
             const int bnd = __shfl_sync(kFull, cv, 0) - lane;     /* slot i belongs to row 0 iff 32*i < bnd */
@@ -373,8 +373,7 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowsplit_kernel(const sbla
             if (pos < cce) t0 = fma(S.val[pos], xv[i], t0);
             if (pos + 32 < cce) t1 = fma(S.val[pos + 32], xv[i + 1], t1);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty0 + 8u * s);                /* the stage goes back to the producer */
+        release_after(empty0 + 8u * s, lane, t0 + t1);              /* the stage goes back once its values are in registers */
 
         if (has_next) {
             mbar_wait(full0 + 8u * sn, phn);

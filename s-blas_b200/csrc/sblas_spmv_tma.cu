@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
                     if (e < lsplit) sc += pr; else so += pr;
                 }
             }
-            release_stage(eb, lane);                           /* slot fully consumed: every warp hands it back */
+            release_after(eb, lane, sc + so);                  /* slot consumed (values in registers): hand it back */
             if (has_next) {
                 mbar_wait(full0 + 8u * sn, phn);
                 gather(st[sn], base + step);                   /* in flight during the reduction */
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(kThreadsTma, kCtasPerSm) spmv_tma_kernel(const
                 mine += __shfl_xor_sync(kFull, mine, 2);         /* pieces beyond k: unused garbage */
             }
             fence_proxy_async_smem();          /* generic writes to the slot before the next bulk copy */
-            release_stage(eb, lane);
+            release_after(eb, lane, mine);
             if (owner && pc < k) {             /* rows that start and end inside my chunk */
                 if (myrow == a.skip_first) a.edge[0] = mine;
                 else if (myrow == a.skip_last) a.edge[1] = mine;
