@@ -7,7 +7,7 @@ and every GPU count 1..n_gpus it runs
     ./test_spmv f <mtxpath><matrix> <gpu> 1 1 f
 
 scrapes the `m:` and `Average` lines exactly like parse_spmv (run_test.py:29-43) and writes
-results.csv with the labels V1/V2/V3 = baseline/v1/v2.  Extra columns (gflops) are appended
+results.csv with the labels V1/V2/V3 = baseline/v1/v2.  Extra columns (gflops, alg_gbs) are appended
 after the reference's eight so existing readers keep working.
 """
 import os
@@ -55,7 +55,7 @@ def parse_spmv(result):
 
 
 def test_spmv(mtxlist, result_file):
-    result_file.write("kernel, matrix, n_gpu, m, n, nnz, version, time, gflops\n")
+    result_file.write("kernel, matrix, n_gpu, m, n, nnz, version, time, gflops, alg_gbs\n")
     for mtx in mtxlist:
         for gpu in range(1, n_gpus + 1):
             cmd = "./test_spmv f " + mtxpath + mtx + " " + str(gpu) + " 1 " + "1 f"
@@ -63,8 +63,11 @@ def test_spmv(mtxlist, result_file):
             result = subprocess.run(cmd, shell=True, capture_output=True, text=True, cwd=HERE).stdout
             m, n, nnz, v1_time, v2_time, v3_time = parse_spmv(result)
             for label, t in (("V1", v1_time), ("V2", v2_time), ("V3", v3_time)):
-                result_file.write("spmv, %s, %d, %d, %d, %d, %s, %s, %s\n" % (
-                    mtx, gpu, m, n, nnz, label, t, (2.0 * nnz / t / 1e9) if t == t and t > 0 else "nan"))
+                ok = t == t and t > 0
+                alg = 12.0 * nnz + 4.0 * (m + 1) + 8.0 * n + 16.0 * m       # BASELINE.md section 2 (beta != 0)
+                result_file.write("spmv, %s, %d, %d, %d, %d, %s, %s, %s, %s\n" % (
+                    mtx, gpu, m, n, nnz, label, t, (2.0 * nnz / t / 1e9) if ok else "nan",
+                    (alg / t / 1e9) if ok else "nan"))
     result_file.write("\n")
 
 
