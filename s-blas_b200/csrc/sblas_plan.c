@@ -313,6 +313,7 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
     int rc = 0;
     long long *stage64 = NULL;
     int *d_stats = NULL, *h_stats = NULL, stats_cap = 0;      /* row-block statistics scratch */
+    int *d_mm = NULL;                                         /* column range scratch */
     const int dry = (src_flags & SBLAS_LAYOUT_ONLY) != 0;     /* host layout only: no CUDA call at all */
     P->dry = dry;
     if (build_global(P, rp) != 0) { sblas_set_error("%s%s (line %d)", "partition failed", "", __LINE__); return -1; }
@@ -431,13 +432,13 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
         /* the window of x this shard reads: [col_lo, col_hi] (one reduction over col at plan time) */
         D->col_lo = 0; D->col_hi = P->n - 1;
         if (D->nnz > 0 && env_int("SBLAS_X_WINDOW", 1)) {
-            int *d_mm = NULL, h_mm[2] = {0x7fffffff, -1};
+            int h_mm[2] = {0x7fffffff, -1};
             CU(cudaMalloc((void **)&d_mm, 2 * sizeof(int)));
             CU(cudaMemcpyAsync(d_mm, h_mm, sizeof h_mm, cudaMemcpyHostToDevice, st));
             CU(sblas_launch_col_range(D->d_col, D->nnz, d_mm, st));
             CU(cudaMemcpyAsync(h_mm, d_mm, sizeof h_mm, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
-            cudaFree(d_mm);
+            cudaFree(d_mm); d_mm = NULL;
             if (h_mm[0] >= 0 && h_mm[1] < P->n && h_mm[0] <= h_mm[1]) { D->col_lo = h_mm[0]; D->col_hi = h_mm[1]; }
         }
 
@@ -664,6 +665,7 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
 fail:
     if (stage64) cudaFree(stage64);
     if (d_stats) cudaFree(d_stats);
+    if (d_mm) cudaFree(d_mm);
     free(h_stats);
     return rc;
 }
