@@ -93,3 +93,28 @@ def test_golden_known_answers(qh768):
         p = sb.partition_v1(qh768["rowptr"], int(g))
         got = [[int(p[k][i]) for k in KEYS[:6]] for i in range(int(g))]
         assert got == rows
+
+
+def test_layout_only_plan_lists_one_panel_per_segment():
+    """Without a GPU (SBLAS_LAYOUT_ONLY) a plan cannot bin rows (the statistics are computed on the
+    device), so every live segment is exactly one panel that covers its rows and entries; the panel
+    accessors of the C-ABI work on such plans."""
+    import sblas_b200 as sb
+    rng = np.random.default_rng(3)
+    lens = np.concatenate([rng.integers(1, 9, size=400), [5000, 0, 0, 3000], rng.integers(50, 90, size=100)])
+    rp = np.zeros(len(lens) + 1, np.int64)
+    np.cumsum(lens, out=rp[1:])
+    m, nnz = len(lens), int(rp[-1])
+    col = np.zeros(nnz, np.int32)
+    val = np.ones(nnz)
+    for version, world, nb, q in ((sb.V1, 3, 0, 1), (sb.V2, 2, nnz // 7 + 1, 2), (sb.BASELINE, 4, 0, 1)):
+        for rank in range(world):
+            p = sb.Plan.create_rank(version, m, m, nnz, val, rp, col, world, rank, 0, kernel=1, nb=nb, q=q,
+                                    flags=sb.LAYOUT_ONLY)
+            segs = p.local_segments()
+            units = p.units()
+            assert len(units) == len(segs)
+            for u, s in zip(units, segs):
+                assert (u["row_lo"], u["row_hi"], u["nz0"], u["nz1"]) == (s["row_lo"], s["row_hi"], s["nz0"], s["nz1"])
+                assert u["kind"] in (1, 3)          # lanes-per-row below 65,536 entries per GPU, else the TMA kernel
+            p.destroy()
