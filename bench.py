@@ -3,24 +3,37 @@
 1/2/4/8 B200, for the hot path of pnnl/s-blas named by BASELINE.json.
 
     python bench.py --gpus N --steps K --warmup W [--workload NAME] [--impl reference]
-    (N > 1: launched by torchrun, one rank per GPU, NCCL)
+    (N > 1: launched by torchrun, one rank per GPU, NCCL for the plumbing)
 
 A step is one SpMV of the named synthetic matrix, sharded with the reference's v1
 nnz-balanced partition (spmv/src/dspmv_mgpu_v1.cu:59-100) over the N ranks (strong
-scaling: the matrix is fixed).  Per step every rank launches the tile kernel + its fix-up
-on its resident shard; for N > 1 the raw partial sums of rows split between ranks (<= 2
-doubles per rank) are all-gathered (NCCL) and each owner finishes its split rows in
-ascending rank order.  value = 2*nnz / max-over-ranks step time.
+scaling: the matrix is fixed).  Per step every rank launches its row panels' kernels on its
+resident shard; for N > 1 the raw partial sums of rows split between ranks (<= 2 doubles per
+rank) are exchanged by the fused P2P publish/merge kernels and each owner finishes its split
+rows in ascending rank order.  value = 2*nnz / max-over-ranks step time.
+
+The JSON line of the default run carries, beside the headline workload (BASELINE config 2):
+  configs        the other BASELINE configs (3 circuit5m, 4 rail4284, 5 big50m) measured in the same
+                 job at the same N: ms/step, GFLOP/s, algorithmic GB/s, full-vector parity, clocks
+  inprocess_api  (N > 1, rank 0) the reference's own single-process entry points
+                 spMV_mgpu_baseline/_v1/_v2(..., ngpu=N) and the chained plan driven over all N GPUs
+                 of the node from one process, full-vector check against the oracle
+  reference_gpu  whole-call time of the reference's stock one-shot path (its unmodified sources,
+                 oracle/_ref/libref_spmv.so) against this library's one-shot entry point on the same
+                 host arrays
 
 Timing: CUDA events on the plan's own stream, W >= 3 warm-up steps, exactly K timed steps
-between barrier + synchronize, max over ranks.  The inputs (>= 14 GB at the default
-workload) are far larger than the 126 MB L2, so no flush is needed between iterations.
+between barrier + synchronize, max over ranks.  The inputs of the large workloads (>= 14 GB) are far
+larger than the 126 MB L2; the small ones (circuit5m 0.8 GB, rail4284 0.14 GB) are still larger than L2
+but rail4284's per-GPU shard at N >= 2 is not: `config.l2` says which.
 
-The oracle (oracle/) is used here only (a) to CHECK a sample of rows of the result before
-timing and (b) as the timed CPU baseline (cpu_baseline, and the whole of --impl reference).
+The oracle (oracle/) is used here only (a) to CHECK the result before timing -- the FULL vector at
+full size, every rank its own rows, split rows finished across ranks -- and (b) as the timed CPU
+baseline (cpu_baseline, and the whole of --impl reference).
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -36,12 +49,13 @@ ALPHA, BETA = 0.8401877171547095, 0.39438292681909304      # the harness's ALPHA
 if os.environ.get("SBLAS_BENCH_BETA"):                      # diagnostics only
     BETA = float(os.environ["SBLAS_BENCH_BETA"])
 SEED = 20260318
+EXTRA_CONFIGS = ("big50m", "circuit5m", "rail4284")        # BASELINE configs 5, 3, 4 (config 2 is the headline)
+COLS_PREFIX, COLS_BANDED, COLS_UNIFORM, COLS_CIRCUIT, COLS_BANDRUN = 0, 1, 2, 3, 4     # include/sblas_synth.h
 
 
 # ----------------------------------------------------------------------------- workloads
 def workload(name):
     """Returns dict(m, n, row_len (callable -> int64 array of length m), cols_mode, band, desc)."""
-    import sblas_b200 as sb
 
     def two_block(m, n1, l1, l2):
         def f():
@@ -53,57 +67,61 @@ def workload(name):
 
     if name == "g1m":          # BASELINE config 2, reading 2b
         m = 1_000_000
-        return dict(m=m, n=m, row_len=two_block(m, m // 8, 9000, 100), cols_mode=sb.COLS_PREFIX, band=0,
+        return dict(m=m, n=m, row_len=two_block(m, m // 8, 9000, 100), cols_mode=COLS_PREFIX, band=0,
                     desc="test_spmv g shape at n=1,000,000 rows, densities scaled 1/100 (125,000 rows x 9,000 nnz + "
                          "875,000 rows x 100 nnz = 1,212,500,000 nnz, cols 0..k-1 per row; the literal g 1000000 "
                          "would be 1.2e11 nnz = 1.46 TB)")
     if name == "g100000":      # BASELINE config 2, reading 2a: the literal generator at the largest feasible n
         m = 100_000
-        return dict(m=m, n=m, row_len=two_block(m, m // 8, 90000, 1000), cols_mode=sb.COLS_PREFIX, band=0,
+        return dict(m=m, n=m, row_len=two_block(m, m // 8, 90000, 1000), cols_mode=COLS_PREFIX, band=0,
                     desc="test_spmv g 100000 (12,500 rows x 90,000 nnz + 87,500 rows x 1,000 nnz = 1,212,500,000 nnz)")
+    if name == "inproc":       # the matrix of the in-process API / one-shot legs: g shape, 145.5 M nnz
+        m = 200_000
+        return dict(m=m, n=m, row_len=two_block(m, m // 8, 5400, 60), cols_mode=COLS_PREFIX, band=0,
+                    desc="test_spmv g shape at n=200,000 rows (25,000 rows x 5,400 nnz + 175,000 rows x 60 nnz = 145,500,000 nnz)")
     if name == "big50m":       # BASELINE config 5
         m = 50_000_000
-        return dict(m=m, n=m, row_len=two_block(m, m // 8, 180, 2), cols_mode=sb.COLS_BANDRUN, band=1 << 20,
+        return dict(m=m, n=m, row_len=two_block(m, m // 8, 180, 2), cols_mode=COLS_BANDRUN, band=1 << 20,
                     desc="50M-row ~1.2B-nnz non-uniform (6.25M rows x 180 nnz + 43.75M rows x 2 nnz), banded columns "
                          "+-2^20 in runs of 16 consecutive columns")
     if name == "big50m_scatter":
         m = 50_000_000
-        return dict(m=m, n=m, row_len=two_block(m, m // 8, 180, 2), cols_mode=sb.COLS_BANDED, band=1 << 20,
+        return dict(m=m, n=m, row_len=two_block(m, m // 8, 180, 2), cols_mode=COLS_BANDED, band=1 << 20,
                     desc="50M-row ~1.2B-nnz non-uniform, banded columns +-2^20, every entry in its own cache line "
                          "(adversarial for the L1 gather path)")
     if name == "big50m_uniform":
         m = 50_000_000
-        return dict(m=m, n=m, row_len=two_block(m, m // 8, 180, 2), cols_mode=sb.COLS_UNIFORM, band=0,
+        return dict(m=m, n=m, row_len=two_block(m, m // 8, 180, 2), cols_mode=COLS_UNIFORM, band=0,
                     desc="50M-row ~1.2B-nnz non-uniform, uniform columns (adversarial x traffic)")
     if name == "rows180":      # diagnostic: the long-row block of big50m alone
         m = 6_250_000
-        return dict(m=m, n=50_000_000, row_len=two_block(m, m, 180, 180), cols_mode=sb.COLS_BANDRUN, band=1 << 20,
+        return dict(m=m, n=50_000_000, row_len=two_block(m, m, 180, 180), cols_mode=COLS_BANDRUN, band=1 << 20,
                     desc="diagnostic: 6.25M rows x 180 nnz, banded runs")
     if name == "rows100":      # diagnostic: the short-row block of g1m alone (x12 rows to fill the GPU)
         m = 10_500_000
-        return dict(m=m, n=1_000_000, row_len=two_block(m, m, 100, 100), cols_mode=sb.COLS_PREFIX, band=0,
+        return dict(m=m, n=1_000_000, row_len=two_block(m, m, 100, 100), cols_mode=COLS_PREFIX, band=0,
                     desc="diagnostic: 10.5M rows x 100 nnz, prefix columns")
     if name == "rows9000":     # diagnostic: the long-row block of g1m alone
         m = 125_000
-        return dict(m=m, n=1_000_000, row_len=two_block(m, m, 9000, 9000), cols_mode=sb.COLS_PREFIX, band=0,
+        return dict(m=m, n=1_000_000, row_len=two_block(m, m, 9000, 9000), cols_mode=COLS_PREFIX, band=0,
                     desc="diagnostic: 125,000 rows x 9,000 nnz, prefix columns")
     if name == "rows9000b":    # diagnostic: long rows with banded-run columns (x from L2, not L1)
         m = 125_000
-        return dict(m=m, n=50_000_000, row_len=two_block(m, m, 9000, 9000), cols_mode=sb.COLS_BANDRUN, band=1 << 20,
+        return dict(m=m, n=50_000_000, row_len=two_block(m, m, 9000, 9000), cols_mode=COLS_BANDRUN, band=1 << 20,
                     desc="diagnostic: 125,000 rows x 9,000 nnz, banded runs")
     if name == "rows180p":     # diagnostic: rows of 180 with prefix columns (x from L1)
         m = 6_250_000
-        return dict(m=m, n=1_000_000, row_len=two_block(m, m, 180, 180), cols_mode=sb.COLS_PREFIX, band=0,
+        return dict(m=m, n=1_000_000, row_len=two_block(m, m, 180, 180), cols_mode=COLS_PREFIX, band=0,
                     desc="diagnostic: 6.25M rows x 180 nnz, prefix columns")
     if name == "rows1000":     # diagnostic: the short-row block of g100000 alone (x12 rows)
         m = 1_050_000
-        return dict(m=m, n=1_000_000, row_len=two_block(m, m, 1000, 1000), cols_mode=sb.COLS_PREFIX, band=0,
+        return dict(m=m, n=1_000_000, row_len=two_block(m, m, 1000, 1000), cols_mode=COLS_PREFIX, band=0,
                     desc="diagnostic: 1.05M rows x 1,000 nnz, prefix columns")
     if name == "rows2":        # diagnostic: the short-row block of big50m alone
         m = 43_750_000
-        return dict(m=m, n=50_000_000, row_len=two_block(m, m, 2, 2), cols_mode=sb.COLS_BANDRUN, band=1 << 20,
+        return dict(m=m, n=50_000_000, row_len=two_block(m, m, 2, 2), cols_mode=COLS_BANDRUN, band=1 << 20,
                     desc="diagnostic: 43.75M rows x 2 nnz, banded runs")
-    if name == "circuit5m":    # BASELINE config 3
+    if name == "circuit5m":    # BASELINE config 3: nnz target 59,524,291 +-0.5 %
         m = 5_558_326
 
         def f():
@@ -114,59 +132,40 @@ def workload(name):
             hubs = rng.choice(m, size=12, replace=False)
             ln[hubs] = np.array([1_290_000, 620_000, 410_000, 300_000, 240_000, 200_000, 170_000, 150_000,
                                  130_000, 120_000, 110_000, 105_000])
-            return ln
-        return dict(m=m, n=m, row_len=f, cols_mode=sb.COLS_CIRCUIT, band=1 << 16,
-                    desc="Circuit5M-shaped power law (5,558,326 rows, ~59.5M nnz, max row 1.29M, 80% banded / 20% uniform columns)")
-    if name == "rail4284":     # BASELINE config 4
+            # trim to the SuiteSparse figure: the tail of the power law is noisy, so the total is set
+            # by lengthening / shortening the rows of 8..64 entries one entry at a time
+            target, total = 59_524_291, int(ln.sum())
+            mid = np.nonzero((ln >= 8) & (ln <= 64))[0]
+            d = target - total
+            if d != 0 and len(mid) > 0:
+                reps, rest = divmod(abs(d), len(mid))
+                ln[mid] += int(np.sign(d)) * reps
+                ln[mid[:rest]] += int(np.sign(d))
+            return np.maximum(ln, 1)
+        return dict(m=m, n=m, row_len=f, cols_mode=COLS_CIRCUIT, band=1 << 16,
+                    desc="Circuit5M-shaped power law (5,558,326 rows, 59.52M nnz, max row 1.29M, 80% banded / 20% uniform columns)")
+    if name == "rail4284":     # BASELINE config 4: nnz target 11,279,748 +-1 %
         m, n = 4284, 1_092_610
 
         def f():
             rng = np.random.default_rng(SEED + 1)
-            ln = np.exp(rng.normal(7.45, 0.95, size=m)).astype(np.int64) + 1
-            return np.clip(ln, 1, 56_000)
-        return dict(m=m, n=n, row_len=f, cols_mode=sb.COLS_UNIFORM, band=0,
-                    desc="rail4284-shaped short-wide (4,284 x 1,092,610, ~11.3M nnz, log-normal row lengths, uniform columns)")
+            ln = np.exp(rng.normal(7.45, 0.95, size=m))
+            ln = np.clip(ln, 1, 56_000)
+            ln = np.clip(np.floor(ln * (11_279_748 / ln.sum())), 1, 56_000).astype(np.int64)       # mean 2,633
+            ln[np.argmax(ln)] = 56_000
+            return ln
+        return dict(m=m, n=n, row_len=f, cols_mode=COLS_UNIFORM, band=0,
+                    desc="rail4284-shaped short-wide (4,284 x 1,092,610, 11.28M nnz, log-normal row lengths, max 56k, uniform columns)")
     raise SystemExit("unknown workload " + name)
 
 
-def host_sample(wl, frac_rows):
-    """A bounded row sample of the workload on the HOST for the CPU legs: every block of the
-    two-block shapes keeps its share of rows; values uniform(0,1).  Only PREFIX-column shapes
-    (the g generator) are sampled structurally; other shapes take the first rows."""
-    import sblas_b200 as sb
-    lens = wl["row_len"]()
-    m = len(lens)
-    take = max(8, int(m * frac_rows))
-    idx = np.unique(np.linspace(0, m - 1, take).astype(np.int64))
-    sl = lens[idx]
-    rp = np.zeros(len(sl) + 1, np.int64)
-    rp[1:] = np.cumsum(sl)
-    nnz = int(rp[-1])
-    rng = np.random.default_rng(SEED)
-    val = rng.random(nnz)
-    if wl["cols_mode"] == sb.COLS_PREFIX:
-        col = (np.arange(nnz, dtype=np.int64) - np.repeat(rp[:-1], sl)).astype(np.int32)
-    else:
-        col = rng.integers(0, wl["n"], size=nnz, dtype=np.int64).astype(np.int32)
-    x = rng.random(wl["n"])
-    y = rng.random(len(sl))
-    return rp, col, val, x, y
-
-
-def time_cpu(rp, col, val, x, y, reps, fn_name):
-    import oracle
-    L = oracle.lib()
-    fn = getattr(L, fn_name)
-    m = len(rp) - 1
-    yy = y.copy()
-    nt = fn(m, rp, col, val, x, ALPHA, BETA, yy)          # warm-up
-    best = 1e30
-    for _ in range(reps):
-        yy[:] = y
-        t0 = time.perf_counter()
-        fn(m, rp, col, val, x, ALPHA, BETA, yy)
-        best = min(best, time.perf_counter() - t0)
-    return best, (nt if fn_name != "oracle_csr_spmv" else 1)
+def config_of(name, wl, m, n, nnz, world):
+    """The workload description both arms print (identical keys and values for --impl reference)."""
+    per_gpu = (12.0 * nnz + 20.0 * m) / max(world, 1) + 8.0 * min(n, nnz)
+    l2 = ("inputs (%.2f GB per GPU and step) exceed the 126 MB L2; no flush" % (per_gpu / 1e9)) if per_gpu > 200e6 else \
+         ("the per-GPU shard (%.0f MB) fits the 126 MB L2: an L2-resident configuration, reported as such" % (per_gpu / 1e6))
+    return {"workload": wl["desc"], "name": name, "m": m, "n": n, "nnz": nnz,
+            "partition": "v1 nnz-balanced x%d" % world, "alpha": ALPHA, "beta": BETA, "l2": l2}
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -180,7 +179,7 @@ class ClockSampler:
         self.lines = []
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -191,66 +190,613 @@ class ClockSampler:
         for line in self.p.stdout:
             self.lines.append((time.time(), line.strip()))
 
-    def stop(self, t0, t1):
+    def wait_first(self, timeout=3.0):
+        t_w = time.time()
+        while self.p is not None and not self.lines and time.time() - t_w < timeout:
+            time.sleep(0.05)
+
+    def window(self, t0, t1):
+        """Clock record of the wall-clock window [t0, t1] (the sampler keeps running)."""
         if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.12)
         sm, mx, reasons = [], [], set()
-        for ts, ln in self.lines:
+        for ts, ln in list(self.lines):
             f = [c.strip() for c in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
                 mx.append(float(f[2]))
-                if t0 - 0.05 <= ts <= t1 + 0.15:
+                if t0 - 0.02 <= ts <= t1 + 0.06:
                     sm.append(float(f[1]))
                     for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                         if v.lower().startswith("active"):
                             reasons.add(name)
             except ValueError:
                 pass
-        if not sm:      # timed window shorter than the sampling period: use every sample taken under load
-            for ts, ln in self.lines:
-                f = [c.strip() for c in ln.split(",")]
-                try:
-                    if ts >= t0 - 3.0:
-                        sm.append(float(f[1]))
-                except (ValueError, IndexError):
-                    pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+    def close(self):
+        if self.p is not None:
+            self.p.terminate()
 
 
 # ----------------------------------------------------------------------------- reference arm
 def run_reference(args, rank, world):
-    """--impl reference: the reference has no CPU SpMV of its own and its GPU path does not
-    compile against CUDA 12.9, so this arm times the oracle restatement
-    of its csrmv semantics on all host cores, on a bounded row sample of the same workload."""
+    """--impl reference: the reference has no CPU SpMV of its own, so this arm times the
+    oracle restatement of its csrmv semantics on ALL host cores (thread count set explicitly: torchrun
+    exports OMP_NUM_THREADS=1), on the same workload -- the whole matrix, built on the host by the
+    host twin of the GPU generator, when it fits host memory, else a stated row sample."""
     if rank != 0:
         return
-    wl = workload(args.workload)
-    rp, col, val, x, y = host_sample(wl, args.cpu_sample)
+    import oracle
+    cores = oracle.set_threads()
+    name = args.workload
+    wl = workload(name)
+    m, n = wl["m"], wl["n"]
+    lens = wl["row_len"]()
+    rp = np.zeros(m + 1, np.int64)
+    np.cumsum(lens, out=rp[1:])
     nnz = int(rp[-1])
-    for _ in range(args.warmup):
-        time_cpu(rp, col, val, x, y, 1, "oracle_csr_spmv_omp_balanced")
-    t0 = time.perf_counter()
-    best, cores = time_cpu(rp, col, val, x, y, args.steps, "oracle_csr_spmv_omp_balanced")
-    wall = (time.perf_counter() - t0) / max(args.steps, 1)
-    gf = 2.0 * nnz / best / 1e9
-    sample = "%d of %d rows (%.0f%%, every block keeps its share), %d nnz" % (len(rp) - 1, wl["m"], 100 * args.cpu_sample, nnz)
+    frac = args.cpu_sample
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 0
+    if frac <= 0:
+        frac = 1.0 if avail > 2.5 * (12.0 * nnz + 8.0 * (m + n)) else 0.1
+    if frac >= 1.0:
+        rows = m
+        rps = rp
+        sample = "the whole matrix (%d rows, %d nnz), built on the host by the same generator" % (m, nnz)
+    else:
+        # a contiguous share of every row-length block keeps the shape: rows [0, f*m/8) + [m/8, m/8 + f*7m/8)
+        a, b = max(8, int(m // 8 * frac)), max(8, int((m - m // 8) * frac))
+        idx = np.concatenate([np.arange(a), m // 8 + np.arange(b)])
+        rows = len(idx)
+        rps = np.zeros(rows + 1, np.int64)
+        np.cumsum(lens[idx], out=rps[1:])
+        sample = "%d of %d rows (%.0f%% of every row-length block), %d nnz" % (rows, m, 100 * frac, int(rps[-1]))
+    snnz = int(rps[-1])
+    val, col = oracle.synth_fill_csr(rps, 0, 0, snnz, n, wl["cols_mode"], wl["band"], SEED)
+    x = oracle.synth_fill_uniform(n, SEED + 7)
+    y0 = oracle.synth_fill_uniform(rows, SEED + 9)
+    L = oracle.lib()
+    y = y0.copy()
+    for _ in range(max(args.warmup, 1)):
+        y[:] = y0
+        L.oracle_csr_spmv_omp_balanced(rows, rps, col, val, x, ALPHA, BETA, y)
+    ts = []
+    for _ in range(max(args.steps, 1)):
+        y[:] = y0
+        t0 = time.perf_counter()
+        L.oracle_csr_spmv_omp_balanced(rows, rps, col, val, x, ALPHA, BETA, y)
+        ts.append(time.perf_counter() - t0)
+    mean = float(np.mean(ts))
+    gf = 2.0 * snnz / mean / 1e9
     print(json.dumps({
         "impl": "reference", "metric": "double CSR SpMV GFLOP/s", "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": best * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "name": args.workload, "alpha": ALPHA, "beta": BETA},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e3 * (nnz / max(snnz, 1)),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_of(name, wl, m, n, nnz, world),
         "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample,
-                         "gbs": (12.0 * nnz + 20.0 * (len(rp) - 1)) / best / 1e9, "wall_ms_per_step": wall * 1e3},
+                         "gbs": (12.0 * snnz + 20.0 * rows) / mean / 1e9, "best_ms": float(np.min(ts)) * 1e3,
+                         "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"),
+                         "note": "oracle restatement of csrmv (the reference has no CPU SpMV), OpenMP over nnz-balanced row chunks"},
         "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 # ----------------------------------------------------------------------------- our arm
+KNAMES = {1: "spmv_vec_kernel", 2: "spmv_tile_kernel + spmv_tile_fixup", 3: "spmv_tma_kernel + spmv_tile_fixup",
+          4: "spmv_vecp_kernel", 5: "spmv_short_kernel", 6: "spmv_rowtile_kernel", 7: "spmv_rowsplit_kernel"}
+
+
+class Problem:
+    """One workload resident on this rank: shard generated on the GPU, plan, split-row exchange."""
+
+    def __init__(self, name, args, rank, world, local):
+        import torch
+        import torch.distributed as dist
+        import sblas_b200 as sb
+        self.name, self.rank, self.world, self.local = name, rank, world, local
+        self.wl = wl = workload(name)
+        self.m, self.n = m, n = wl["m"], wl["n"]
+        self.lens = lens = wl["row_len"]()
+        self.rp = rp = np.zeros(m + 1, np.int64)
+        np.cumsum(lens, out=rp[1:])
+        self.nnz = nnz = int(rp[-1])
+        version = sb.V1
+        self.parts = parts = sb.partition_v1(rp, world)
+        self.s_idx, self.e_idx = int(parts["start_idx"][rank]), int(parts["end_idx"][rank])
+        self.s_row, self.e_row = int(parts["start_row"][rank]), int(parts["end_row"][rank])
+        self.dnnz = dnnz = self.e_idx - self.s_idx + 1
+        # ---- this rank's shard, generated on the GPU (synthetic, deterministic)
+        self.d_val = torch.empty(dnnz, dtype=torch.float64, device="cuda")
+        self.d_col = torch.empty(dnnz, dtype=torch.int32, device="cuda")
+        d_rp = torch.from_numpy(rp[self.s_row:self.e_row + 2]).cuda()
+        sb.synth_fill_csr(d_rp.data_ptr(), self.s_row, self.e_row - self.s_row + 1, self.s_idx, self.e_idx + 1, n,
+                          wl["cols_mode"], wl["band"], SEED, self.d_val.data_ptr(), self.d_col.data_ptr())
+        torch.cuda.synchronize()
+        del d_rp
+        self.plan = plan = sb.Plan.create_rank(version, m, n, nnz, self.d_val.data_ptr(), rp, self.d_col.data_ptr(),
+                                               world, rank, local, kernel=args.kernel, flags=sb.SRC_DEVICE_SHARD,
+                                               keep=(self.d_val, self.d_col))
+        self.y_ptr, self.first_row, self.rows = plan.y_ptr()
+        sb.synth_fill_uniform(plan.x_ptr(), n, SEED + 7, 0.0, 1.0)
+        sb.synth_fill_uniform(self.y_ptr, self.rows, SEED + 9, 0.0, 1.0)
+        sb.device_synchronize()
+        self.stream = torch.cuda.ExternalStream(plan.stream())
+        slots = plan.edge_slots
+        self.edge = torch.zeros(max(slots, 1), dtype=torch.float64, device="cuda")
+        self.table = torch.zeros(world * max(slots, 1), dtype=torch.float64, device="cuda")
+        self.exchange = "none"
+        self.sbuf = None
+        if world > 1 and slots:
+            self.exchange = args.exchange
+            if self.exchange == "symm":
+                try:
+                    import torch.distributed._symmetric_memory as symm
+                    tw = world * slots
+                    self.sbuf = symm.empty(2 * tw + 2 * world, dtype=torch.float64, device=torch.device("cuda", local))
+                    self.sbuf.zero_()
+                    hdl = symm.rendezvous(self.sbuf, dist.group.WORLD)
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    plan.bind_peer_tables(list(hdl.buffer_ptrs), tw)
+                except Exception as ex:          # no peer mapping available: fall back to NCCL
+                    if rank == 0:
+                        print("symmetric memory unavailable (%s); using NCCL all-gather" % ex, file=sys.stderr)
+                    self.exchange = "nccl"
+            if self.exchange == "nccl":
+                plan.bind_edge_table(self.edge.data_ptr())
+        self.launches_per_step = plan.launches + (2 if self.exchange == "symm" else 1 if self.exchange == "nccl" else 0)
+
+    def step(self):
+        import torch.distributed as dist
+        self.plan.execute_device(ALPHA, BETA)
+        if self.exchange == "symm":
+            self.plan.exchange_merge(ALPHA, BETA)
+        elif self.exchange == "nccl":
+            dist.all_gather_into_tensor(self.table, self.edge)
+            self.plan.merge_gathered(self.table.data_ptr(), ALPHA, BETA)
+
+    def x_touched(self, row_lo=None, row_hi=None):
+        """distinct columns a row range reads (algorithmic x bytes)."""
+        wl, n = self.wl, self.n
+        row_lo = self.s_row if row_lo is None else row_lo
+        row_hi = self.e_row if row_hi is None else row_hi
+        if wl["cols_mode"] == COLS_PREFIX:
+            return min(int(self.lens[row_lo:row_hi + 1].max()), n)
+        if wl["band"] and wl["cols_mode"] in (COLS_BANDRUN, COLS_BANDED):
+            return min(n, (row_hi - row_lo + 1) + 2 * wl["band"])
+        return n
+
+    def alg_bytes(self):
+        return self.plan.alg_bytes(True, self.x_touched())
+
+    def destroy(self):
+        import torch
+        self.plan.destroy()
+        self.d_val = self.d_col = self.edge = self.table = self.sbuf = None
+        torch.cuda.empty_cache()
+
+
+def full_check(P, keep_host=False):
+    """Parity before timing: the FULL result vector of this rank's rows at full size against the oracle
+    (all host cores), split rows finished across ranks in ascending rank order like the library does.
+    Returns (record, host arrays or None)."""
+    import torch
+    import torch.distributed as dist
+    import oracle
+    import sblas_b200 as sb
+    oracle.set_threads()
+    rows, n, dnnz = P.rows, P.n, P.dnnz
+    assert P.first_row == P.s_row, (P.first_row, P.s_row)
+    y0 = np.empty(rows)
+    sb.memcpy(y0, P.y_ptr, 8 * rows, 2)
+    xh = np.empty(n)
+    sb.memcpy(xh, P.plan.x_ptr(), 8 * n, 2)
+    with torch.cuda.stream(P.stream):
+        P.step()
+    torch.cuda.synchronize()
+    if P.world > 1:
+        dist.barrier()
+    y1 = np.empty(rows)
+    sb.memcpy(y1, P.y_ptr, 8 * rows, 2)
+    sb.memcpy(P.y_ptr, y0, 8 * rows, 1)                     # restore the input for the timed steps
+    lrp = np.clip(P.rp[P.s_row:P.s_row + rows + 1] - P.s_idx, 0, dnnz)
+    sf = bool(P.parts["start_flag"][P.rank]) and P.world > 1
+    ef = bool(P.parts["end_flag"][P.rank]) and P.world > 1
+    # the shard comes down to the host in row chunks sized to the free host memory (one chunk when it fits)
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 8 << 30
+    budget = max(1 << 24, int(0.35 * avail / 12.0))
+    worst, wrow, edge = 0.0, -1, np.zeros(4)
+    host = None
+    r0 = 0
+    while r0 < rows:
+        r1 = rows if dnnz - int(lrp[r0]) <= budget else max(r0 + 1, int(np.searchsorted(lrp, lrp[r0] + budget, side="right")) - 1)
+        k0, k1 = int(lrp[r0]), int(lrp[r1])
+        val, col = np.empty(k1 - k0), np.empty(k1 - k0, np.int32)
+        if k1 > k0:
+            sb.memcpy(val, P.d_val.data_ptr() + 8 * k0, 8 * (k1 - k0), 2)
+            sb.memcpy(col, P.d_col.data_ptr() + 4 * k0, 4 * (k1 - k0), 2)
+        sub = np.ascontiguousarray(lrp[r0:r1 + 1] - k0)
+        w, wr, e = oracle.csr_check(sub, col, val, xh, ALPHA, BETA, y0[r0:r1], y1[r0:r1],
+                                    0 if (sf and r0 == 0) else -1, (r1 - r0 - 1) if (ef and r1 == rows) else -1)
+        if sf and r0 == 0:
+            edge[0:2] = e[0:2]
+        if ef and r1 == rows:
+            edge[2:4] = e[2:4]
+        if not w <= worst:
+            worst, wrow = w, r0 + wr
+        if r0 == 0 and r1 == rows and keep_host:
+            host = (lrp, col, val, xh, y0)
+        r0 = r1
+    split_checked = 0
+    if P.world > 1:
+        contrib = []
+        if sf:
+            contrib.append((P.s_row, float(edge[0]), float(edge[1])))
+        if ef and not (sf and rows == 1):
+            contrib.append((P.s_row + rows - 1, float(edge[2]), float(edge[3])))
+        allc = [None] * P.world
+        dist.all_gather_object(allc, contrib)
+        by_row = {}
+        for r in range(P.world):
+            for row, s, b in allc[r]:
+                by_row.setdefault(row, []).append((r, s, b))
+        for row, lst in by_row.items():
+            if lst[0][0] != P.rank:            # the row belongs to the rank where it starts
+                continue
+            i = row - P.first_row
+            s = sum(t[1] for t in lst)
+            b = abs(ALPHA) * sum(t[2] for t in lst) + abs(BETA) * abs(y0[i])
+            e = abs(y1[i] - (ALPHA * s + BETA * y0[i])) / b if b > 0 else 0.0
+            split_checked += 1
+            if not e <= worst:
+                worst, wrow = e, i
+    rec = {"rows_checked": int(rows), "split_rows_checked": split_checked, "max_err_over_bound": worst,
+           "worst_row": int(P.first_row + wrow) if wrow >= 0 else None, "tolerance": 1e-12, "ok": bool(worst <= 1e-12),
+           "what": "full vector of this rank's rows vs the oracle at full size"}
+    t = torch.tensor([0.0 if rec["ok"] else 1.0, float(rows), float(split_checked), worst if worst == worst else 1e300],
+                     dtype=torch.float64, device="cuda")
+    if P.world > 1:
+        tm = t.clone()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        rec.update(ok=bool(t[0].item() == 0.0), rows_checked=int(t[1].item()), split_rows_checked=int(t[2].item()),
+                   max_err_over_bound=float(tm[3].item()))
+    return rec, host
+
+
+def barrier(world):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def timed_steps(P, steps, warmup, sampler):
+    """W warm-up + exactly K timed steps on the plan's stream between barrier + synchronize.
+    Returns (ms per step = max over ranks of total/K, per-step ms of this rank, clock record)."""
+    import torch
+    import torch.distributed as dist
+    stream = P.stream
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            P.step()
+    barrier(P.world)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    t_wall0 = time.time()
+    with torch.cuda.stream(stream):
+        ev[0].record(stream)
+        for k in range(steps):
+            P.step()
+            ev[k + 1].record(stream)
+    ev[-1].synchronize()
+    barrier(P.world)
+    t_wall1 = time.time()
+    clocks = sampler.window(t_wall0, t_wall1) if sampler else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per = np.array([ev[k].elapsed_time(ev[k + 1]) for k in range(steps)])
+    tt = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if P.world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    return float(tt.item()) / steps, per, clocks
+
+
+def allsum(v, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def allmax(v, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def e2e_measure(P, steps):
+    """End to end through the plan's host API: pinned host x and y in, host y out, every step; wall
+    clock, max over ranks.  One call per product (sblas_spmv_plan_execute: copies, kernels, split-row
+    exchange and the copy back are enqueued together, one synchronisation at the end)."""
+    import torch
+    m, n, world = P.m, P.n, P.world
+    xh_p = torch.empty(n, dtype=torch.float64).pin_memory()
+    yh_p = torch.empty(m, dtype=torch.float64).pin_memory()
+    xh_p.uniform_(0, 1)
+    yh_p.uniform_(0, 1)
+    xh_np, yh_np = xh_p.numpy(), yh_p.numpy()
+
+    def one():
+        if P.exchange == "nccl":           # the NCCL variant needs the caller's collective between the halves
+            P.plan.upload(xh_np, yh_np)
+            with torch.cuda.stream(P.stream):
+                P.step()
+            P.plan.download(yh_np)
+        else:
+            P.plan.execute(ALPHA, xh_np, BETA, yh_np)
+
+    for _ in range(3):
+        one()
+    barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    barrier(world)
+    e2e_s = allmax((time.perf_counter() - t0) / steps, world)
+    xw = P.plan.x_window()                # every rank uploads the window of x its shard references
+    h2d = int(allsum(8.0 * (xw[1] - xw[0] + 1) + 8.0 * P.rows, world))
+    d2h = 8 * m
+    return e2e_s, h2d, d2h
+
+
+def measure(name, args, rank, world, local, sampler, steps, warmup, primary):
+    """Build, check, time one workload at this N.  Every rank runs it; rank 0's record is the one printed."""
+    import torch
+    import oracle                          # checker + CPU baseline only
+    import sblas_b200 as sb
+    P = Problem(name, args, rank, world, local)
+    m, n, nnz = P.m, P.n, P.nnz
+    check, host = (None, None)
+    if not args.no_check:
+        check, host = full_check(P, keep_host=(primary and world == 1 and not args.no_cpu))
+        if not check["ok"]:
+            raise SystemExit("parity check failed for %s on rank %d: %r" % (name, rank, check))
+    # short workloads: enough steps for the 50 ms clock sampler to see the timed window
+    if not primary:
+        with torch.cuda.stream(P.stream):
+            for _ in range(3):
+                P.step()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(P.stream)
+            for _ in range(5):
+                P.step()
+            e1.record(P.stream)
+        e1.synchronize()
+        est = allmax(e0.elapsed_time(e1) / 5.0, world)
+        steps = int(min(20000, max(steps, math.ceil(700.0 / max(est, 1e-3)))))
+    ms_step, per, clocks = timed_steps(P, steps, warmup, sampler)
+    gflops = 2.0 * nnz / (ms_step * 1e-3) / 1e9
+    alg_rank = P.alg_bytes()
+    alg_total = allsum(alg_rank, world)
+    rec = {"name": name, "ms_per_step": ms_step, "gflops": gflops, "steps": steps, "warmup": warmup,
+           "hbm_gbs": alg_total / (ms_step * 1e-3) / 1e9,
+           "hbm_frac_of_8000": alg_total / (ms_step * 1e-3) / 1e9 / (8000.0 * world),
+           "alg_bytes": alg_total, "parity_check": check, "parity_ok": bool(check["ok"]) if check else None,
+           "clocks": clocks, "config": config_of(name, P.wl, m, n, nnz, world),
+           "panels_rank0": [{"kernel": KNAMES.get(u["kind"], "?"), "rows": u["row_hi"] - u["row_lo"] + 1,
+                             "nnz": u["nz1"] - u["nz0"]} for u in P.plan.units()],
+           "gpu_launches_per_step": P.launches_per_step}
+    rec["_per"] = per
+    rec["_alg_rank"] = alg_rank
+    rec["_exchange"] = P.exchange
+
+    # ---- the dominant kernel alone (roofline): the plan's largest row panel, launched by itself
+    units = P.plan.units()
+    dom = max(units, key=lambda u: u["nz1"] - u["nz0"]) if units else None
+    if dom is not None:
+        nrep = max(3, min(steps, 50))
+        with torch.cuda.stream(P.stream):
+            for _ in range(3):
+                P.plan.execute_unit(dom["index"], ALPHA, BETA)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(P.stream)
+            for _ in range(nrep):
+                P.plan.execute_unit(dom["index"], ALPHA, BETA)
+            e1.record(P.stream)
+        e1.synchronize()
+        dom_ms = e0.elapsed_time(e1) / nrep
+        u_nnz, u_rows = dom["nz1"] - dom["nz0"], dom["row_hi"] - dom["row_lo"] + 1
+        dom_alg = 12.0 * u_nnz + 4.0 * (u_rows + 1) + 8.0 * P.x_touched(dom["row_lo"], dom["row_hi"]) + 16.0 * u_rows
+        rec["dominant"] = {"kernel": KNAMES.get(dom["kind"], "?"), "row_lo": dom["row_lo"], "row_hi": dom["row_hi"],
+                           "nnz": u_nnz, "ms": dom_ms, "alg_bytes": dom_alg, "gbs": dom_alg / (dom_ms * 1e-3) / 1e9}
+    barrier(world)
+
+    # ---- end to end
+    e2e_s, h2d, d2h = e2e_measure(P, max(args.e2e_steps, 20 if primary else 10))
+    rec["e2e"] = {"value": 2.0 * nnz / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d,
+                  "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3}
+
+    # ---- CPU baseline beside it (N = 1, headline workload): the oracle on the same arrays, all host cores
+    if primary and world == 1 and not args.no_cpu and host is not None:
+        lrp, col, val, xh, y0 = host
+        L = oracle.lib()
+        cores = oracle.set_threads()
+        yy = y0.copy()
+        L.oracle_csr_spmv_omp_balanced(m, lrp, col, val, xh, ALPHA, BETA, yy)
+        ts = []
+        for _ in range(5):
+            yy[:] = y0
+            t0 = time.perf_counter()
+            L.oracle_csr_spmv_omp_balanced(m, lrp, col, val, xh, ALPHA, BETA, yy)
+            ts.append(time.perf_counter() - t0)
+        take = max(8, m // 20)              # single thread: 5 % of every row-length block (bounded)
+        rows1 = np.concatenate([np.arange(min(take, m // 8)), m // 8 + np.arange(take)])
+        t0 = time.perf_counter()
+        s_nnz = 0
+        for a, b in ((0, min(take, m // 8)), (m // 8, m // 8 + take)):
+            sub = lrp[a:b + 1] - lrp[a]
+            yy2 = y0[a:b].copy()
+            L.oracle_csr_spmv(b - a, np.ascontiguousarray(sub), col[lrp[a]:lrp[b]], val[lrp[a]:lrp[b]], xh, ALPHA, BETA, yy2)
+            s_nnz += int(sub[-1])
+        t_st = time.perf_counter() - t0
+        rec["cpu_baseline"] = {"value": 2.0 * nnz / float(np.mean(ts)) / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "port",
+                               "sample": "the whole matrix (%d rows, %d nnz) on the host, mean of 5 (best %.1f ms)" % (m, nnz, min(ts) * 1e3),
+                               "single_thread_gflops": 2.0 * s_nnz / t_st / 1e9,
+                               "single_thread_sample": "%d rows (5%% of each row-length block), %d nnz" % (len(rows1), s_nnz)}
+    rec["_read_probe"] = None
+    if primary and rank == 0:
+        try:
+            rec["_read_probe"] = sb.synth_read_probe(P.d_val.data_ptr(), 8 * P.dnnz, 3, P.plan.stream())
+        except Exception:
+            pass
+    P.destroy()
+    return rec
+
+
+def host_problem(name):
+    """A workload built on the HOST (numpy arrays, like the reference harness's buffers)."""
+    import oracle
+    wl = workload(name)
+    m, n = wl["m"], wl["n"]
+    lens = wl["row_len"]()
+    rp = np.zeros(m + 1, np.int64)
+    np.cumsum(lens, out=rp[1:])
+    nnz = int(rp[-1])
+    val, col = oracle.synth_fill_csr(rp, 0, 0, nnz, n, wl["cols_mode"], wl["band"], SEED)
+    x = oracle.synth_fill_uniform(n, SEED + 7)
+    y0 = oracle.synth_fill_uniform(m, SEED + 9)
+    return dict(m=m, n=n, nnz=nnz, rp=rp, col=col, val=val, x=x, y0=y0, desc=wl["desc"])
+
+
+def small_host_cases():
+    """qh768 as the harness loads it (committed COO fixture) and the `g 10000` shape."""
+    import oracle
+    out = []
+    g = np.load(os.path.join(ROOT, "tests", "golden", "qh768_coo.npz"))
+    m, n = int(g["m"]), int(g["n"])
+    rp = oracle.coo_to_rowptr(m, g["row"])
+    rng = np.random.default_rng(5)
+    out.append(("qh768", dict(m=m, n=n, nnz=int(rp[-1]), rp=rp, col=np.ascontiguousarray(g["col"]),
+                              val=np.ascontiguousarray(g["val"]), x=rng.uniform(0.5, 1.5, n), y0=rng.standard_normal(m))))
+    gn = 10000
+    lens = np.where(np.arange(gn) < gn // 8, 9000, 100).astype(np.int64)
+    rp = np.zeros(gn + 1, np.int64)
+    np.cumsum(lens, out=rp[1:])
+    nnz = int(rp[-1])
+    val, col = oracle.synth_fill_csr(rp, 0, 0, nnz, gn, COLS_PREFIX, 0, SEED)
+    out.append(("g 10000 shape", dict(m=gn, n=gn, nnz=nnz, rp=rp, col=col, val=val, x=np.ones(gn), y0=np.zeros(gn))))
+    return out
+
+
+def inprocess_api(ngpu):
+    """The reference's own single-process entry points driven over ngpu GPUs of the node from THIS
+    process (what test_spmv does: spmv/test/dspmv_test.cu:314-332,346-440), full-vector check of every
+    call against the oracle; then two chained products on a resident plan (sblas_spmv_plan_chain)."""
+    import oracle
+    import sblas_b200 as sb
+    oracle.set_threads()
+    out = {"ngpu": ngpu, "ok": True, "calls": []}
+    cases = small_host_cases() + [("inproc 145.5M nnz", host_problem("inproc"))]
+    for cname, c in cases:
+        lrp = c["rp"]
+        for entry in ("baseline", "v1 kernel 1", "v1 kernel 2", "v2 kernel 1"):
+            y = c["y0"].copy()
+            a = (c["m"], c["n"], c["nnz"], ALPHA, c["val"], c["rp"], c["col"], c["x"], BETA, y)
+            t0 = time.perf_counter()
+            if entry == "baseline":
+                rc = sb.spMV_mgpu_baseline(*a, ngpu)
+            elif entry.startswith("v1"):
+                rc = sb.spMV_mgpu_v1(*a, ngpu, int(entry[-1]))
+            else:
+                rc = sb.spMV_mgpu_v2(*a, ngpu, 1, max(c["nnz"] // (ngpu * 2), 1), 2)
+            ms = (time.perf_counter() - t0) * 1e3
+            worst, wrow, _ = oracle.csr_check(lrp, c["col"], c["val"], c["x"], ALPHA, BETA, c["y0"], y)
+            ok = rc == 0 and worst <= 1e-12
+            out["calls"].append({"matrix": cname, "entry": entry, "rc": rc, "ms_whole_call": ms,
+                                 "max_err_over_bound": worst, "ok": bool(ok)})
+            out["ok"] = out["ok"] and bool(ok)
+    # chained products on the resident plan of the large case
+    c = cases[-1][1]
+    p = sb.Plan.create(sb.V1, c["m"], c["n"], c["nnz"], c["val"] * (1.0 / 4096.0), c["rp"], c["col"], ngpu, kernel=1)
+    vs = c["val"] * (1.0 / 4096.0)
+    x = c["x"].copy()
+    p.upload(x, None)
+    chain_ok, t_chain = True, []
+    for it in range(3):
+        t0 = time.perf_counter()
+        p.execute_device(1.25, 0.0, sync=False)
+        y = np.zeros(c["m"])
+        p.download(y)
+        t_chain.append((time.perf_counter() - t0) * 1e3)
+        worst, _, _ = oracle.csr_check(c["rp"], c["col"], vs, x, 1.25, 0.0, np.zeros(c["m"]), y)
+        chain_ok = chain_ok and worst <= 1e-12
+        p.chain()
+        x = y
+    sb.device_synchronize()
+    p.destroy()
+    out["chain"] = {"products": 3, "ok": bool(chain_ok), "ms_execute_plus_download": t_chain}
+    out["ok"] = out["ok"] and bool(chain_ok)
+    return out
+
+
+def reference_gpu(ngpu):
+    """GPU-vs-GPU anchor of the drop-in call: whole-call wall time of the reference's stock one-shot
+    path (its own unmodified sources over cuSPARSE, oracle/_ref/libref_spmv.so) against this library's
+    one-shot spMV_mgpu_v1 -- plan cache off and on -- on the same host arrays (145.5 M nnz)."""
+    import oracle
+    import sblas_b200 as sb
+    ref = oracle.ref_spmv()
+    if ref is None:
+        return {"unavailable": "oracle/_ref/libref_spmv.so not built"}
+    c = host_problem("inproc")
+    a = lambda y: (c["m"], c["n"], c["nnz"], ALPHA, c["val"], c["rp"], c["col"], c["x"], BETA, y)
+    out = {"ngpu": ngpu, "matrix": c["desc"], "unit": "ms per whole call (host arrays in, host y out)"}
+
+    def best(fn, reps=3):
+        ts, y = [], None
+        for _ in range(reps):
+            y = c["y0"].copy()
+            t0 = time.perf_counter()
+            rc = fn(y)
+            ts.append((time.perf_counter() - t0) * 1e3)
+            assert rc == 0, rc
+        return min(ts), y
+    t_ref, y_ref = best(lambda y: ref.v1(*a(y), ngpu, 1))
+    t_ref2, _ = best(lambda y: ref.v1(*a(y), ngpu, 2))
+    t_lib, y_lib = best(lambda y: sb.spMV_mgpu_v1(*a(y), ngpu, 1))
+    os.environ["SBLAS_PLAN_CACHE"] = "1"
+    try:
+        t_cache, y_c = best(lambda y: sb.spMV_mgpu_v1(*a(y), ngpu, 1), reps=4)
+    finally:
+        os.environ.pop("SBLAS_PLAN_CACHE", None)
+        sb.cache_clear()
+    w1, _, _ = oracle.csr_check(c["rp"], c["col"], c["val"], c["x"], ALPHA, BETA, c["y0"], y_lib)
+    w2, _, _ = oracle.csr_check(c["rp"], c["col"], c["val"], c["x"], ALPHA, BETA, c["y0"], y_ref)
+    w3, _, _ = oracle.csr_check(c["rp"], c["col"], c["val"], c["x"], ALPHA, BETA, c["y0"], y_c)
+    out.update({"reference_v1_kernel1": t_ref, "reference_v1_kernel2": t_ref2, "sblas_v1_one_shot": t_lib,
+                "sblas_v1_plan_cache": t_cache, "speedup_one_shot": t_ref / t_lib, "speedup_plan_cache": t_ref / t_cache,
+                "max_err_over_bound": {"sblas": w1, "reference": w2, "sblas_cached": w3},
+                "ok": bool(w1 <= 1e-12 and w3 <= 1e-12)})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -259,10 +805,12 @@ def main():
     ap.add_argument("--impl", default="sblas")
     ap.add_argument("--workload", default=os.environ.get("SBLAS_BENCH_WORKLOAD", "g1m"))
     ap.add_argument("--kernel", type=int, default=1)
-    ap.add_argument("--cpu-sample", type=float, default=0.1, help="fraction of rows in the CPU legs' sample")
+    ap.add_argument("--cpu-sample", type=float, default=0.0,
+                    help="--impl reference: fraction of rows (0 = the whole matrix when host memory allows, else 0.1)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs and the API legs")
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--exchange", default="symm", choices=["symm", "nccl"],
                     help="split-row exchange for N>1: fused P2P over symmetric memory, or an NCCL all-gather")
     args = ap.parse_args()
@@ -277,221 +825,44 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import sblas_b200 as sb
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU (no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    wl = workload(args.workload)
-    m, n = wl["m"], wl["n"]
-    lens = wl["row_len"]()
-    rp = np.zeros(m + 1, np.int64)
-    np.cumsum(lens, out=rp[1:])
-    nnz = int(rp[-1])
-    parts = sb.partition_v1(rp, world)
-    s_idx, e_idx = int(parts["start_idx"][rank]), int(parts["end_idx"][rank])
-    s_row, e_row = int(parts["start_row"][rank]), int(parts["end_row"][rank])
-    dnnz = e_idx - s_idx + 1
-
-    # ---- this rank's shard, generated on the GPU (synthetic, deterministic)
-    d_val = torch.empty(dnnz, dtype=torch.float64, device="cuda")
-    d_col = torch.empty(dnnz, dtype=torch.int32, device="cuda")
-    d_rp = torch.from_numpy(rp[s_row:e_row + 2]).cuda()
-    sb.synth_fill_csr(d_rp.data_ptr(), s_row, e_row - s_row + 1, s_idx, e_idx + 1, n, wl["cols_mode"], wl["band"],
-                      SEED, d_val.data_ptr(), d_col.data_ptr())
-    torch.cuda.synchronize()
-    del d_rp
-    plan = sb.Plan.create_rank(sb.V1, m, n, nnz, d_val.data_ptr(), rp, d_col.data_ptr(), world, rank, local,
-                               kernel=args.kernel, flags=sb.SRC_DEVICE_SHARD, keep=(d_val, d_col))
-    y_ptr, first_row, rows = plan.y_ptr()
-    sb.synth_fill_uniform(plan.x_ptr(), n, SEED + 7, 0.0, 1.0)
-    sb.synth_fill_uniform(y_ptr, rows, SEED + 9, 0.0, 1.0)
-    sb.device_synchronize()
-    stream = torch.cuda.ExternalStream(plan.stream())
-    slots = plan.edge_slots
-    edge = torch.zeros(max(slots, 1), dtype=torch.float64, device="cuda")
-    table = torch.zeros(world * max(slots, 1), dtype=torch.float64, device="cuda")
-    exchange = "none"
-    if world > 1 and slots:
-        exchange = args.exchange
-        if exchange == "symm":
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler is not None:
+        sampler.wait_first()
+    extra_on = not args.no_extra and args.workload == "g1m"
+    t_job0 = time.time()
+    main_rec = measure(args.workload, args, rank, world, local, sampler, args.steps, args.warmup, True)
+    extras = []
+    if extra_on:
+        for name in EXTRA_CONFIGS:
             try:
-                import torch.distributed._symmetric_memory as symm
-                tw = world * slots
-                sbuf = symm.empty(2 * tw + 2 * world, dtype=torch.float64, device=torch.device("cuda", local))
-                sbuf.zero_()
-                hdl = symm.rendezvous(sbuf, dist.group.WORLD)
-                torch.cuda.synchronize()
-                dist.barrier()
-                plan.bind_peer_tables(list(hdl.buffer_ptrs), tw)
-            except Exception as ex:          # no peer mapping available: fall back to NCCL
-                if rank == 0:
-                    print("symmetric memory unavailable (%s); using NCCL all-gather" % ex, file=sys.stderr)
-                exchange = "nccl"
-        if exchange == "nccl":
-            plan.bind_edge_table(edge.data_ptr())
-
-    def step():
-        plan.execute_device(ALPHA, BETA)
-        if exchange == "symm":
-            plan.exchange_merge(ALPHA, BETA)
-        elif exchange == "nccl":
-            dist.all_gather_into_tensor(table, edge)
-            plan.merge_gathered(table.data_ptr(), ALPHA, BETA)
-
-    # ---- parity check of a row sample at FULL size, before timing (oracle = checker only)
-    check = None
-    if not args.no_check:
-        import oracle
-        y0 = np.empty(rows)
-        sb.memcpy(y0, y_ptr, 8 * rows, 2)
-        xh = np.empty(n)
-        sb.memcpy(xh, plan.x_ptr(), 8 * n, 2)
-        with torch.cuda.stream(stream):
-            step()
-        torch.cuda.synchronize()
-        y1 = np.empty(rows)
-        sb.memcpy(y1, y_ptr, 8 * rows, 2)
-        rng = np.random.default_rng(rank)
-        skip = 1 if parts["start_flag"][rank] else 0
-        cand = np.arange(s_row + skip, e_row + 1)
-        pick = np.unique(np.concatenate([cand[:3], cand[-3:], rng.choice(cand, size=min(1500, len(cand)), replace=False)]))
-        worst = 0.0
-        for r in pick:
-            b, e = int(rp[r]), int(rp[r + 1])
-            if world == 1 or (b >= s_idx and e - 1 <= e_idx):
-                vv = np.empty(e - b)
-                cc = np.empty(e - b, np.int32)
-                sb.memcpy(vv, d_val.data_ptr() + 8 * (b - s_idx), 8 * (e - b), 2)
-                sb.memcpy(cc, d_col.data_ptr() + 4 * (b - s_idx), 4 * (e - b), 2)
-                lrp = np.array([0, e - b], np.int64)
-                yi = np.array([y0[r - first_row]])
-                want = oracle.csr_spmv(lrp, cc, vv, xh, ALPHA, BETA, yi)[0]
-                bound = oracle.csr_spmv_bound(lrp, cc, vv, xh, ALPHA, BETA, yi)[0]
-                rel = abs(y1[r - first_row] - want) / bound
-                worst = max(worst, rel)
-        check = {"rows_checked": int(len(pick)), "max_err_over_bound": worst, "tolerance": 1e-12, "ok": bool(worst <= 1e-12)}
-        if not check["ok"]:
-            raise SystemExit("parity check failed on rank %d: %r" % (rank, check))
-        sb.memcpy(y_ptr, y0, 8 * rows, 1)
-
-    # ---- timed region
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi needs a moment
-    if sampler is not None and sampler.p is not None and world > 1:
-        t_w = time.time()                                      # the other ranks wait at the barrier below
-        while not sampler.lines and time.time() - t_w < 3.0:
-            time.sleep(0.05)
-    with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            step()
-    barrier()
-    if sampler is not None and sampler.p is not None and world == 1:
-        t_w = time.time()                                      # keep the GPU busy until the first sample arrives
-        while not sampler.lines and time.time() - t_w < 3.0:
-            with torch.cuda.stream(stream):
-                step()
-            torch.cuda.synchronize()
-    barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    t_wall0 = time.time()
-    with torch.cuda.stream(stream):
-        ev[0].record(stream)
-        for k in range(args.steps):
-            step()
-            ev[k + 1].record(stream)
-    ev[-1].synchronize()
-    barrier()
-    t_wall1 = time.time()
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    total_ms = ev[0].elapsed_time(ev[-1])
-    per = np.array([ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)])
-    tt = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_step = float(tt.item()) / args.steps
-    gflops = 2.0 * nnz / (ms_step * 1e-3) / 1e9
-
-    # ---- algorithmic bytes: x_touched = distinct columns a shard reads
-    if wl["cols_mode"] == sb.COLS_PREFIX:
-        x_touched = int(lens.max())
-    elif wl["band"] and wl["cols_mode"] in (sb.COLS_BANDRUN, sb.COLS_BANDED):
-        x_touched = min(n, (e_row - s_row + 1) + 2 * wl["band"])       # this rank's rows plus the band
-    else:
-        x_touched = n
-    alg = torch.tensor([plan.alg_bytes(True, min(x_touched, n))], dtype=torch.float64, device="cuda")
-    alg_rank0 = float(alg.item())
-    if world > 1:
-        dist.all_reduce(alg, op=dist.ReduceOp.SUM)
-    alg_total = float(alg.item())
-
-    # ---- the dominant kernel alone (roofline): the plan's largest row panel, launched by itself
-    KNAMES = {1: "spmv_vec_kernel", 2: "spmv_tile_kernel + spmv_tile_fixup", 3: "spmv_tma_kernel + spmv_tile_fixup",
-              4: "spmv_vecp_kernel", 5: "spmv_short_kernel", 6: "spmv_rowtile_kernel"}
-    units = plan.units()
-    dom = max(units, key=lambda u: u["nz1"] - u["nz0"]) if units else None
-    dom_ms = None
-    if dom is not None:
-        nrep = max(3, min(args.steps, 50))
-        with torch.cuda.stream(stream):
-            for _ in range(3):
-                plan.execute_unit(dom["index"], ALPHA, BETA)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for _ in range(nrep):
-                plan.execute_unit(dom["index"], ALPHA, BETA)
-            e1.record(stream)
-        e1.synchronize()
-        dom_ms = e0.elapsed_time(e1) / nrep
-        u_nnz, u_rows = dom["nz1"] - dom["nz0"], dom["row_hi"] - dom["row_lo"] + 1
-        if wl["cols_mode"] == sb.COLS_PREFIX:
-            u_x = min(int(lens[dom["row_lo"]:dom["row_hi"] + 1].max()), n)
-        elif wl["band"] and wl["cols_mode"] in (sb.COLS_BANDRUN, sb.COLS_BANDED):
-            u_x = min(n, u_rows + 2 * wl["band"])
-        else:
-            u_x = n
-        dom_alg = 12.0 * u_nnz + 4.0 * (u_rows + 1) + 8.0 * u_x + 16.0 * u_rows
-    barrier()
-
-    # ---- end to end: host x, y (pinned) in, host y out, every step
-    xh_p = torch.empty(n, dtype=torch.float64).pin_memory()
-    yh_p = torch.empty(m, dtype=torch.float64).pin_memory()
-    xh_p.uniform_(0, 1)
-    yh_p.uniform_(0, 1)
-    xh_np, yh_np = xh_p.numpy(), yh_p.numpy()
-
-    def e2e_step():
-        if world == 1:                     # the plan's host API: one call, host x and y in, host y out
-            plan.execute(ALPHA, xh_np, BETA, yh_np)
-            return
-        plan.upload(xh_np, yh_np)
-        with torch.cuda.stream(stream):
-            step()
-        plan.download(yh_np)
-
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
-    xw = plan.x_window()                  # every rank uploads the window of x its shard references
-    xb = torch.tensor([8.0 * (xw[1] - xw[0] + 1)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(xb, op=dist.ReduceOp.SUM)
-    h2d = int(xb.item()) + 8 * m         # + the y slices, which add up to m (+ shared rows)
-    d2h = 8 * m
+                r = measure(name, args, rank, world, local, sampler, 60, 5, False)
+                extras.append(r)
+            except SystemExit:
+                raise
+            except Exception as ex:            # a failed extra config must not take the headline with it
+                extras.append({"name": name, "error": repr(ex)})
+                barrier(world)
+    api = None
+    refgpu = None
+    if extra_on:
+        barrier(world)
+        if rank == 0:
+            if world > 1:
+                try:
+                    api = inprocess_api(world)
+                except Exception as ex:
+                    api = {"ngpu": world, "ok": False, "error": repr(ex)}
+            try:
+                refgpu = reference_gpu(world)
+            except Exception as ex:
+                refgpu = {"error": repr(ex)}
+        barrier(world)
 
     if rank == 0:
         peaks = {}
@@ -500,58 +871,73 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        # dominant kernel = spmv_tile_kernel on rank 0's shard; its launch (+ the few-us fix-up) is the N=1 step
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured read+write copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        r = main_rec
+        per = r.pop("_per")
+        alg_rank0 = r.pop("_alg_rank")
+        exchange = r.pop("_exchange")
+        read_peak = r.pop("_read_probe")
         k_ms = float(np.median(per)) if world == 1 else None
         step_ach = alg_rank0 / (float(np.mean(per)) * 1e-3) / 1e9
-        ach = dom_alg / (dom_ms * 1e-3) / 1e9 if dom_ms else step_ach
-        dom_name = KNAMES.get(dom["kind"], "?") if dom else "?"
+        dom = r.get("dominant")
+        ach = dom["gbs"] if dom else step_ach
         traffic = None            # dram bytes read+written per launch from the committed ncu capture, if any
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             traffic = tr.get("%s:n%d" % (args.workload, world), {}).get("dram_bytes_per_launch")
         except Exception:
             pass
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "read_peak": read_peak, "frac_of_read_peak": (ach / read_peak) if read_peak and read_peak > 0 else None,
+                "note": ("frac > 1 is possible against the driver's peak, which is a read+write COPY: this kernel is ~99% reads; "
+                         "read_peak is a read-only streaming probe measured in this run and is the honest ceiling"),
+                "kernel": "%s on rank 0's largest row panel (rows %d..%d, %d nnz), timed alone" % (
+                    dom["kernel"], dom["row_lo"], dom["row_hi"], dom["nnz"]) if dom else None,
+                "alg_bytes_per_launch": dom["alg_bytes"] if dom else None, "ms_per_launch_mean": dom["ms"] if dom else None,
+                "share_of_step": (dom["ms"] / float(np.mean(per))) if dom else None,
+                "whole_step": {"achieved": step_ach, "frac": step_ach / peak, "alg_bytes": alg_rank0,
+                               "ms_mean": float(np.mean(per)), "ms_median": k_ms, "panels": r["panels_rank0"]}}
+        cfg = dict(r["config"])
         out = {
-            "metric": "double CSR SpMV GFLOP/s", "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["desc"], "name": args.workload, "m": m, "n": n, "nnz": nnz,
-                       "partition": "v1 nnz-balanced x%d" % world, "kernel": args.kernel, "exchange": exchange, "alpha": ALPHA, "beta": BETA,
-                       "l2": "inputs (%.1f GB per step) far exceed the 126 MB L2; no flush" % (alg_total / 1e9)},
-            "hbm_gbs": alg_total / (ms_step * 1e-3) / 1e9,
-            "hbm_frac_of_8000": alg_total / (ms_step * 1e-3) / 1e9 / (8000.0 * world),
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "%s on rank 0's largest row panel (rows %d..%d, %d nnz), timed alone" % (
-                             dom_name, dom["row_lo"], dom["row_hi"], dom["nz1"] - dom["nz0"]) if dom else None,
-                         "alg_bytes_per_launch": dom_alg if dom else None, "ms_per_launch_mean": dom_ms,
-                         "share_of_step": (dom_ms / float(np.mean(per))) if dom_ms else None,
-                         "whole_step": {"achieved": step_ach, "frac": step_ach / peak, "alg_bytes": alg_rank0,
-                                        "ms_mean": float(np.mean(per)), "ms_median": k_ms,
-                                        "panels": [{"kernel": KNAMES.get(u["kind"], "?"), "rows": u["row_hi"] - u["row_lo"] + 1,
-                                                    "nnz": u["nz1"] - u["nz0"]} for u in units]}},
-            "e2e": {"value": 2.0 * nnz / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
-                    "api": ("sblas_spmv_plan_execute on a resident plan (host x, y in; host y out; y slices of the row panels "
-                            "move while other panels compute)") if world == 1 else
-                           "sblas_spmv_plan_upload + execute_device + fused split-row exchange + download on a resident plan"},
-            "gpu_launches": args.steps * (plan.launches + (2 if exchange == "symm" else 1 if exchange == "nccl" else 0)),
-            "clocks": clocks, "parity_check": check,
+            "metric": "double CSR SpMV GFLOP/s", "value": r["gflops"], "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "impl_config": {"kernel": args.kernel, "exchange": exchange},
+            "hbm_gbs": r["hbm_gbs"], "hbm_frac_of_8000": r["hbm_frac_of_8000"], "roofline": roof,
+            "e2e": dict(r["e2e"], api="sblas_spmv_plan_execute on a resident plan: host x (the columns the shard reads) and y in, "
+                                      "kernels + split-row exchange, host y out, one call and one synchronisation per product"),
+            "gpu_launches": args.steps * r["gpu_launches_per_step"],
+            "clocks": r["clocks"], "parity_check": r["parity_check"],
         }
-        if not args.no_cpu and world == 1:
-            rps, cols, vals, xs, ys = host_sample(wl, args.cpu_sample)
-            snnz = int(rps[-1])
-            t_mt, cores = time_cpu(rps, cols, vals, xs, ys, 5, "oracle_csr_spmv_omp_balanced")
-            t_st, _ = time_cpu(rps, cols, vals, xs, ys, 2, "oracle_csr_spmv")
-            out["cpu_baseline"] = {"value": 2.0 * snnz / t_mt / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "port",
-                                   "sample": "%d of %d rows (every block keeps its share), %d nnz, best of 5" % (len(rps) - 1, m, snnz),
-                                   "single_thread_gflops": 2.0 * snnz / t_st / 1e9}
+        if "cpu_baseline" in r:
+            out["cpu_baseline"] = r["cpu_baseline"]
+        if extras:
+            out["configs"] = []
+            for e in extras:
+                if "error" in e:
+                    out["configs"].append(e)
+                    continue
+                for k in ("_per", "_alg_rank", "_exchange", "_read_probe"):
+                    e.pop(k, None)
+                d = e.get("dominant")
+                out["configs"].append({
+                    "name": e["name"], "ms_per_step": e["ms_per_step"], "gflops": e["gflops"], "steps": e["steps"],
+                    "hbm_gbs": e["hbm_gbs"], "whole_step_frac": e["hbm_gbs"] / (peak * world),
+                    "hbm_frac_of_8000": e["hbm_frac_of_8000"], "parity_ok": e["parity_ok"], "parity_check": e["parity_check"],
+                    "clocks": e["clocks"], "e2e": e["e2e"], "dominant": d, "panels_rank0": e["panels_rank0"],
+                    "config": e["config"]})
+        if api is not None:
+            out["inprocess_api"] = api
+        if refgpu is not None:
+            out["reference_gpu"] = refgpu
+        out["job_wall_s"] = time.time() - t_job0
         print(json.dumps(out))
+    if sampler is not None:
+        sampler.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    plan.destroy()
 
 
 if __name__ == "__main__":

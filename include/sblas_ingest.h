@@ -17,7 +17,8 @@ extern "C" {
 #endif
 
 /* sizes of the CSR the file expands to.  returns 0; -1 cannot open; -2 bad banner; -4 bad size
- * line; -5 short or malformed entry list (mmio_highlevel.h:21,26,39 use the same codes) */
+ * line; -5 short or malformed entry list (mmio_highlevel.h:21,26,39 use the same codes); -6 out of memory;
+ * -7 a symmetric / hermitian file that is not square (the mirrored entries would fall outside the matrix) */
 int sblas_mtx_info(const char *path, int *m, int *n, long long *nnz, int *is_symmetric);
 
 /* fill csrRowPtr[m+1], csrColIndex[nnz], csrVal[nnz] (caller-allocated from sblas_mtx_info) */

@@ -111,8 +111,10 @@ int sblas_spmv_plan_create_rank(sblas_spmv_plan **plan, int version, int m, int 
 /* y = alpha*A*x + beta*y with HOST x (length n) and HOST y (length m, in/out):
  * uploads x (and y when beta != 0), runs every segment, downloads y and merges
  * the split boundary rows in ascending segment order. In a rank plan only this
- * rank's rows of y are written; rows shared with other ranks are left to
- * sblas_spmv_plan_edges / the caller's exchange. */
+ * rank's rows of y are written; rows shared with other ranks are finished by the fused
+ * exchange when peer tables are bound (sblas_spmv_plan_bind_peer_tables: then every rank
+ * must make this call once per product), else left to sblas_spmv_plan_edges / the caller's
+ * exchange. */
 int sblas_spmv_plan_execute(sblas_spmv_plan *plan, const double *alpha, const double *x,
                             const double *beta, double *y);
 

@@ -33,6 +33,12 @@ int sblas_synth_fill_csr(const long long *d_rowptr, int row_first, int nrows, lo
 /* p[i] = lo + (hi-lo)*u(seed,i) */
 int sblas_synth_fill_uniform(double *d_p, long long count, unsigned long long seed, double lo, double hi, void *stream);
 
+/* Read-only HBM bandwidth of this GPU in GB/s (measurement support for bench.py's roofline: the
+ * driver's measured peak is a read+write copy, which a read-dominated kernel can exceed): best of
+ * `reps` passes of a plain 128-bit streaming-load kernel over `bytes` of device memory at d_buf,
+ * timed with CUDA events on `stream`.  < 0 on failure. */
+double sblas_synth_read_probe(const void *d_buf, unsigned long long bytes, int reps, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

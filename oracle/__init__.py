@@ -4,7 +4,8 @@ ctypes front-end of oracle/spmv_oracle.c (the CPU restatement of the s-BLAS
 multi-GPU CSR SpMV path; see that file's header for the parity status and the
 reference file:line each function follows) and of oracle/_ref/libref_helper.so
 (the reference's own spmv/src/spmv_helper.cu compiled where it lies by
-oracle/Makefile).
+oracle/Makefile) and oracle/_ref/libref_spmv.so (the reference's own, unmodified
+three entry points over a cusparseDcsrmv -> cusparseSpMV compat header; GPU only).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 reference legs may import this package.
@@ -71,8 +72,61 @@ def lib():
         L.oracle_load_mtx.argtypes = [C.c_char_p, C.c_char, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                       C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_load_mtx.restype = C.c_int
+        L.oracle_set_threads.argtypes = [C.c_int]
+        L.oracle_set_threads.restype = C.c_int
+        L.oracle_csr_check.argtypes = [C.c_int, _pl, _pi, _pd, _pd, C.c_double, C.c_double, _pd, _pd, C.c_int, C.c_int,
+                                       _pd, C.POINTER(C.c_int)]
+        L.oracle_csr_check.restype = C.c_double
+        L.oracle_synth_fill_csr.argtypes = [_pl, C.c_int, C.c_int, _LL, _LL, C.c_int, C.c_int, _LL, C.c_ulonglong,
+                                            C.c_int, C.c_double, _pd, _pi]
+        L.oracle_synth_fill_csr.restype = None
+        L.oracle_synth_fill_uniform.argtypes = [_pd, _LL, C.c_ulonglong, C.c_double, C.c_double]
+        L.oracle_synth_fill_uniform.restype = None
         _lib = L
     return _lib
+
+
+def host_cores():
+    """Cores this process may run on (the affinity mask, not a launcher's OMP_NUM_THREADS)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def set_threads(n=None):
+    """Set the OpenMP thread count of the CPU legs explicitly (default: every core of the affinity
+    mask) -- torchrun exports OMP_NUM_THREADS=1 to its ranks.  Returns the count in force."""
+    return lib().oracle_set_threads(int(n) if n else host_cores())
+
+
+def csr_check(local_rowptr, col, val, x, alpha, beta, y_in, y_got, skip_first=-1, skip_last=-1):
+    """Full-vector check of one shard on all cores.  Returns (worst |err|/bound over the rows that are not
+    skipped, its row, edge = [sum_first, bound_first, sum_last, bound_last] raw partials of the skipped rows)."""
+    edge = np.zeros(4)
+    wr = C.c_int(-1)
+    w = lib().oracle_csr_check(len(local_rowptr) - 1, _c(local_rowptr, np.int64), _c(col, np.int32), _c(val, np.float64),
+                               _c(x, np.float64), alpha, beta, _c(y_in, np.float64), _c(y_got, np.float64),
+                               int(skip_first), int(skip_last), edge, C.byref(wr))
+    return float(w), int(wr.value), edge
+
+
+def synth_fill_csr(rowptr_slice, row_first, k0, k1, n, cols_mode, band, seed, value_const=None):
+    """Host twin of sblas_synth_fill_csr: val/col of the global entry range [k0, k1) of the rows
+    [row_first, row_first + len(rowptr_slice) - 1) whose int64 row pointer slice is given."""
+    rp = _c(rowptr_slice, np.int64)
+    val = np.empty(k1 - k0, np.float64)
+    col = np.empty(k1 - k0, np.int32)
+    lib().oracle_synth_fill_csr(rp, int(row_first), len(rp) - 1, int(k0), int(k1), int(n), int(cols_mode), int(band),
+                                int(seed), 0 if value_const is None else 1, 0.0 if value_const is None else float(value_const),
+                                val, col)
+    return val, col
+
+
+def synth_fill_uniform(count, seed, lo=0.0, hi=1.0):
+    out = np.empty(count, np.float64)
+    lib().oracle_synth_fill_uniform(out, int(count), int(seed), lo, hi)
+    return out
 
 
 _ref = None
@@ -91,6 +145,56 @@ def ref_helper():
         f.restype = C.c_int
         _ref = f
     return _ref
+
+
+_ref_spmv = None
+
+
+def ref_spmv():
+    """The reference's OWN three entry points -- spmv/src/dspmv_mgpu_{baseline,v1,v2}.cu + spmv_helper.cu,
+    unmodified, compiled where they lie with oracle/compat_csrmv.h force-included (legacy
+    cusparseDcsrmv[_mp] -> cusparseSpMV) into oracle/_ref/libref_spmv.so -- or None when the library
+    was not built.  Needs a GPU to run.  Returns an object with baseline / v1 / v2 taking the
+    reference's argument list (numpy host arrays, y updated in place) and returning its status code
+    (v2's is undefined in the reference: it falls off the end)."""
+    global _ref_spmv
+    if _ref_spmv is not None:
+        return _ref_spmv
+    p = os.path.join(_HERE, "_ref", "libref_spmv.so")
+    if not os.path.exists(p):
+        return None
+    R = C.CDLL(p)                       # RTLD_LOCAL + -Bsymbolic: its mangled names never meet the product's
+    vp = C.c_void_p
+    mg = [C.c_int, C.c_int, _LL, vp, vp, vp, vp, vp, vp, vp, C.c_int]
+    fb = getattr(R, "_Z18spMV_mgpu_baselineiixPdS_PxPiS_S_S_i")
+    f1 = getattr(R, "_Z12spMV_mgpu_v1iixPdS_PxPiS_S_S_ii")
+    f2 = getattr(R, "_Z12spMV_mgpu_v2iixPdS_PxPiS_S_S_iixi")
+    fb.argtypes = mg
+    f1.argtypes = mg + [C.c_int]
+    f2.argtypes = mg + [C.c_int, _LL, C.c_int]
+
+    class Ref:
+        path = p
+
+        @staticmethod
+        def _call(fn, m, n, nnz, alpha, val, rp, col, x, beta, y, *extra):
+            a, b = C.c_double(alpha), C.c_double(beta)
+            for arr, dt in ((val, np.float64), (rp, np.int64), (col, np.int32), (x, np.float64), (y, np.float64)):
+                assert arr.dtype == dt and arr.flags["C_CONTIGUOUS"]
+            return fn(m, n, nnz, C.addressof(a), val.ctypes.data, rp.ctypes.data, col.ctypes.data, x.ctypes.data,
+                      C.addressof(b), y.ctypes.data, *extra)
+
+        def baseline(self, m, n, nnz, alpha, val, rp, col, x, beta, y, ngpu):
+            return self._call(fb, m, n, nnz, alpha, val, rp, col, x, beta, y, ngpu)
+
+        def v1(self, m, n, nnz, alpha, val, rp, col, x, beta, y, ngpu, kernel):
+            return self._call(f1, m, n, nnz, alpha, val, rp, col, x, beta, y, ngpu, kernel)
+
+        def v2(self, m, n, nnz, alpha, val, rp, col, x, beta, y, ngpu, kernel, nb, q):
+            return self._call(f2, m, n, nnz, alpha, val, rp, col, x, beta, y, ngpu, kernel, int(nb), q)
+
+    _ref_spmv = Ref()
+    return _ref_spmv
 
 
 # ----------------------------------------------------------------------------- wrappers

@@ -411,3 +411,138 @@ int oracle_load_mtx(const char *path, char mode, int *m, int *n, int *nnz,
     fclose(f);
     return 0;
 }
+
+/* ------------------------------------------------------------------------- */
+/* Helpers of bench.py's checker / CPU legs (not restatements of reference code). */
+
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs set their thread count explicitly
+ * (all cores of the affinity mask) and report it.  Returns the value now in force. */
+int oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
+/* Full-vector check of a shard, all rows in parallel: want = alpha*A*x + beta*y_in (rows summed left
+ * to right, as oracle_csr_spmv), err_i = |y_got[i] - want_i| / (|alpha| sum|a||x| + |beta||y_in[i]|).
+ * rowptr is the shard's LOCAL row pointer (rowptr[0] = 0).  Rows skip_first / skip_last (shard-local
+ * index, or -1) are rows split with another shard: left out of the maximum; their raw partial sums and
+ * partial bounds are returned in edge[0..3] = {sum_first, bound_first, sum_last, bound_last} so that the
+ * caller can finish them across shards.  Returns the worst err; *worst_row = its row. */
+double oracle_csr_check(int m, const ll *rowptr, const int *col, const double *val, const double *x,
+                        double alpha, double beta, const double *y_in, const double *y_got,
+                        int skip_first, int skip_last, double *edge, int *worst_row)
+{
+    double worst = 0.0;
+    int wrow = -1;
+#ifdef _OPENMP
+#pragma omp parallel
+#endif
+    {
+        double lw = 0.0;
+        int lr = -1;
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 4096) nowait
+#endif
+        for (int i = 0; i < m; ++i) {
+            double s = 0.0, b = 0.0;
+            for (ll k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+                const double p = val[k] * x[col[k]];
+                s += p;
+                b += fabs(p);
+            }
+            if (i == skip_first) { edge[0] = s; edge[1] = b; continue; }
+            if (i == skip_last) { edge[2] = s; edge[3] = b; continue; }
+            const double want = alpha * s + beta * y_in[i];
+            const double bound = fabs(alpha) * b + fabs(beta) * fabs(y_in[i]);
+            const double d = fabs(y_got[i] - want);
+            const double e = bound > 0.0 ? d / bound : (d == 0.0 ? 0.0 : INFINITY);
+            if (!(e <= lw)) { lw = e; lr = i; }         /* NaN counts as worst */
+        }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        {
+            if (!(lw <= worst)) { worst = lw; wrow = lr; }
+            else if (wrow < 0) wrow = lr;
+        }
+    }
+    if (worst_row) *worst_row = wrow;
+    return worst;
+}
+
+/* The synthetic matrices of bench.py on the HOST: the same hash generator as the GPU one
+ * (s-blas_b200/csrc/sblas_synth.cu: splitmix64 of (seed, entry index); column patterns PREFIX 0,
+ * BANDED 1, UNIFORM 2, CIRCUIT 3, BANDRUN 4), restated here so that the reference arm can build the
+ * workload without a GPU.  tests/ checks the two generators agree entry for entry. */
+static inline unsigned long long o_mix64(unsigned long long z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static inline double o_u01(unsigned long long h) { return ((double)(h >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+
+void oracle_synth_fill_csr(const ll *rp, int row_first, int nrows, ll k0, ll k1, int n, int mode, ll band,
+                           unsigned long long seed, int vmode, double vconst, double *val, int *col)
+{
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1024)
+#endif
+    for (int i = 0; i < nrows; ++i) {
+        const ll b = rp[i], e = rp[i + 1];
+        if (e <= k0 || b >= k1) continue;
+        const ll len = e - b, row = (ll)row_first + i;
+        int m = mode;
+        if (m == 3) {
+            const int hub = (o_mix64(seed ^ (unsigned long long)row * 0x51ull) % 5u) == 0u;
+            m = (hub || len > 2 * band) ? 2 : 1;
+        }
+        ll W = n, start = 0;
+        const int runs = (m == 4);
+        if (runs) m = 1;
+        if (m == 1) {
+            W = 2 * band < n ? 2 * band : n;
+            if (W < len) W = len < n ? len : n;
+            start = row - W / 2;
+            if (start < 0) start = 0;
+            if (start + W > n) start = n - W;
+        }
+        const ll jb = (b > k0 ? b : k0) - b, je = (e < k1 ? e : k1) - b;
+        for (ll j = jb; j < je; ++j) {
+            const ll k = b + j;
+            const unsigned long long h = o_mix64(seed ^ (unsigned long long)k);
+            int c;
+            if (m == 0) c = (int)(j < n ? j : n - 1);
+            else if (runs && len <= W / 16) {
+                const ll nrun = (len + 15) / 16, r = j / 16;
+                const unsigned long long hr = o_mix64(seed ^ (unsigned long long)(b + r * 16) * 0x9E37ull);
+                const ll cell = (W / 16) / nrun;
+                const ll slot = r * cell + (ll)(hr % (unsigned long long)cell);
+                const ll cc = start + slot * 16 + (j - r * 16);
+                c = (int)(cc < n ? cc : n - 1);
+            } else if (len <= W) {
+                const ll lo = (ll)(((__int128)j * W) / len), hi = (ll)(((__int128)(j + 1) * W) / len);
+                const ll span = hi - lo > 0 ? hi - lo : 1;
+                c = (int)(start + lo + (ll)(h % (unsigned long long)span));
+            } else c = (int)(j % n);
+            col[k - k0] = c;
+            val[k - k0] = vmode ? vconst : o_u01(o_mix64(h));
+        }
+    }
+}
+
+void oracle_synth_fill_uniform(double *p, ll count, unsigned long long seed, double lo, double hi)
+{
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (ll i = 0; i < count; ++i)
+        p[i] = lo + (hi - lo) * o_u01(o_mix64(seed ^ (unsigned long long)i * 0x2545F4914F6CDD1Dull));
+}

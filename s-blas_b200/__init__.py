@@ -133,6 +133,8 @@ def lib():
     L.sblas_synth_fill_csr.argtypes = [_vp, C.c_int, C.c_int, _LL, _LL, C.c_int, C.c_int, _LL, C.c_ulonglong,
                                        C.c_int, C.c_double, _vp, _vp, _vp]
     L.sblas_synth_fill_uniform.argtypes = [_vp, _LL, C.c_ulonglong, C.c_double, C.c_double, _vp]
+    L.sblas_synth_read_probe.argtypes = [_vp, C.c_ulonglong, C.c_int, _vp]
+    L.sblas_synth_read_probe.restype = C.c_double
     _lib = L
     return L
 
@@ -473,3 +475,8 @@ def synth_fill_uniform(d_p, count, seed, lo=0.0, hi=1.0, stream=None):
     rc = lib().sblas_synth_fill_uniform(int(d_p), int(count), int(seed), lo, hi, stream)
     if rc != 0:
         raise RuntimeError("sblas_synth_fill_uniform: cuda error %d" % rc)
+
+
+def synth_read_probe(d_buf, nbytes, reps=3, stream=None):
+    """Read-only HBM bandwidth (GB/s) of a streaming-load kernel over nbytes of device memory."""
+    return lib().sblas_synth_read_probe(int(d_buf), int(nbytes), int(reps), stream)

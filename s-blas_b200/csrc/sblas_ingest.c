@@ -39,6 +39,9 @@ static int read_head(FILE *f, mtx_head *h)
         if (!fgets(line, sizeof line, f)) return -4;
     }
     if (h->m <= 0 || h->n <= 0 || h->listed < 0) return -4;
+    /* a symmetric / hermitian file must be square: the mirrored entry (j, i) is written into row j,
+     * which does not exist when n > m (untrusted input: reject instead of writing past the row pointer) */
+    if (h->symmetric && h->m != h->n) return -7;
     return 0;
 }
 

@@ -41,6 +41,8 @@ typedef struct sblas_dev {
     cudaStream_t copy_stream;         /* second stream: y slices move while other panels compute */
     cudaEvent_t *ev_unit; int nev_unit; /* per panel: its y slice is on the GPU / its kernel is done */
     cudaEvent_t ev_y, ev_chain;       /* y complete on this GPU / this GPU has pulled every y slice (chain) */
+    cudaEvent_t ev_merge, ev_xpull;   /* this GPU's merge has read its peers' edge tables / has pulled its peers' x slices */
+    int merge_recorded, xpull_recorded;
     int kind, ipt;
     long long xs_lo, xs_hi;           /* slice of x this GPU uploads itself */
     int col_lo, col_hi;               /* smallest / largest column of the resident shard: the x it reads */
@@ -57,6 +59,7 @@ struct sblas_spmv_plan {
     int nunits, cap_units; sblas_unit *units;
     sblas_dev *devs;
     const double *gather_base;
+    int cap_pieces; int *piece_lo, *piece_hi, *piece_unit;    /* pieces of the pipelined host execute */
     /* fused exchange over peer-mapped memory */
     int peer_bound, nout, nowners, ncontrib;
     unsigned long long epoch;

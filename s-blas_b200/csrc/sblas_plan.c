@@ -125,6 +125,8 @@ static void free_dev(sblas_dev *D, int dry)
     free(D->ev_unit);
     if (D->ev_y) cudaEventDestroy(D->ev_y);
     if (D->ev_chain) cudaEventDestroy(D->ev_chain);
+    if (D->ev_merge) cudaEventDestroy(D->ev_merge);
+    if (D->ev_xpull) cudaEventDestroy(D->ev_xpull);
     free(D->streams); free(D->ev_seg);
     free(D->h_mrow); free(D->h_mbeg); free(D->h_msrc); free(D->h_msrc_off);
 }
@@ -139,6 +141,7 @@ void sblas_spmv_plan_destroy(sblas_spmv_plan *P)
     }
     free(P->devs); free(P->segs); free(P->units); free(P->parts); free(P->g_owner); free(P->g_local);
     free(P->g_lo); free(P->g_hi); free(P->g_sf); free(P->g_sl);
+    free(P->piece_lo); free(P->piece_hi); free(P->piece_unit);
     free(P);
 }
 
@@ -403,6 +406,8 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
         CU(cudaEventCreateWithFlags(&D->ev_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&D->ev_y, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&D->ev_chain, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&D->ev_merge, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&D->ev_xpull, cudaEventDisableTiming));
         cudaStream_t st = D->streams[0];
         (void)st;
 
@@ -749,6 +754,11 @@ static int enqueue_segments(sblas_spmv_plan *P, int d, double alpha, double beta
     sblas_dev *D = &P->devs[d];
     if (D->seg_begin < 0) return 0;
     CU(cudaSetDevice(D->device));
+    /* in-process multi-GPU: the segments below overwrite this GPU's edge table, which the other GPUs'
+     * merge kernels of the PREVIOUS product read over NVLink: wait for those merges first */
+    if (!P->rank_mode && P->ndev > 1)
+        for (int o = 0; o < P->ndev; ++o)
+            if (o != d && P->devs[o].merge_recorded) CU(cudaStreamWaitEvent(D->streams[0], P->devs[o].ev_merge, 0));
     if (D->nstreams > 1) {
         CU(cudaEventRecord(D->ev_in, D->streams[0]));
         for (int c = 1; c < D->nstreams; ++c) CU(cudaStreamWaitEvent(D->streams[c], D->ev_in, 0));
@@ -787,6 +797,10 @@ static int enqueue_merge(sblas_spmv_plan *P, int d, double alpha, double beta)
             if (o != d && P->devs[o].seg_begin >= 0) CU(cudaStreamWaitEvent(D->streams[0], P->devs[o].ev_done, 0));
     CU(sblas_launch_edge_merge(D->d_mrow, D->d_mbeg, (const double *const *)D->d_msrc, D->nmerge, D->d_y,
                                alpha, beta, D->streams[0]));
+    if (!P->rank_mode && P->ndev > 1) {
+        CU(cudaEventRecord(D->ev_merge, D->streams[0]));
+        D->merge_recorded = 1;
+    }
 fail:
     return rc;
 }
@@ -848,6 +862,9 @@ int sblas_spmv_plan_upload(sblas_spmv_plan *P, const double *x, const double *y)
         long long lo = (long long)P->n * li / live, hi = (long long)P->n * (li + 1) / live;
         if (live == 1) { lo = D->col_lo; hi = (long long)D->col_hi + 1; }     /* only what the shard reads */
         D->xs_lo = lo; D->xs_hi = hi;
+        if (x && live > 1)              /* peers may still be pulling the previous x out of this replica */
+            for (int o = 0; o < nd; ++o)
+                if (o != d && P->devs[o].xpull_recorded) CU(cudaStreamWaitEvent(st, P->devs[o].ev_xpull, 0));
         if (x && hi > lo)
             CU(cudaMemcpyAsync(D->d_x + lo, x + lo, (size_t)(hi - lo) * sizeof(double), cudaMemcpyHostToDevice, st));
         if (y)
@@ -868,9 +885,9 @@ int sblas_spmv_plan_upload(sblas_spmv_plan *P, const double *x, const double *y)
                 CU(cudaMemcpyPeerAsync(D->d_x + O->xs_lo, D->device, O->d_x + O->xs_lo, O->device,
                                        (size_t)(O->xs_hi - O->xs_lo) * sizeof(double), D->streams[0]));
             }
+            CU(cudaEventRecord(D->ev_xpull, D->streams[0]));     /* the next upload on every peer waits for this */
+            D->xpull_recorded = 1;
         }
-        /* nobody may start overwriting d_x (next upload) before every peer has pulled: the
-         * execute that follows records ev_done per GPU and the download synchronises */
     }
 fail:
     return rc;
@@ -963,9 +980,16 @@ fail:
     return rc;
 }
 
-/* One GPU, one segment, several row panels: the y slice of panel u+1 goes up and the finished
- * slice of panel u-1 comes down on a second stream while panel u computes; only the first panel's
- * upload and the last panel's download are exposed. */
+/* One GPU, one segment (a one-GPU plan, or one rank of a multi-process job): the product is cut into
+ * PIECES -- its row panels, the row-aligned ones (short / medium / long-medium kernels) cut further
+ * into runs of ~128 Ki rows -- and the y slice of piece p+1 goes up and the finished slice of piece p-1
+ * comes down on a second stream while piece p computes; only the first piece's upload and the last
+ * piece's download are exposed.  (At N GPUs the reference's nnz-balanced split leaves most ROWS on
+ * the last shard -- 875 k of g1m's 1 M rows at N = 8 -- so without this the last rank's 7 MB of y each
+ * way over PCIe would double the product time.)  The split-row exchange of a rank plan runs after the
+ * last piece; the row it finishes is that piece's last row. */
+#define SBLAS_PIECE_ROWS (128 * 1024)
+#define SBLAS_PIECE_MAX 16
 static int execute_pipelined(sblas_spmv_plan *P, double alpha, const double *x, double beta, double *y)
 {
     int rc = 0;
@@ -974,45 +998,94 @@ static int execute_pipelined(sblas_spmv_plan *P, double alpha, const double *x, 
     const int nu = S->unit_end - S->unit_begin;
     CU(cudaSetDevice(D->device));
     if (!D->copy_stream) CU(cudaStreamCreateWithFlags(&D->copy_stream, cudaStreamNonBlocking));
-    if (D->nev_unit < 2 * nu) {
-        cudaEvent_t *ev = (cudaEvent_t *)calloc((size_t)2 * nu, sizeof(cudaEvent_t));
+    /* count the pieces */
+    int npiece = 0;
+    for (int u = 0; u < nu; ++u) {
+        const sblas_unit *U = &P->units[S->unit_begin + u];
+        const long long rows = (long long)U->args.row_hi - U->args.row_lo + 1;
+        int k = 1;
+        if ((U->kind == SBLAS_K_SHORT || U->kind == SBLAS_K_ROWTILE || U->kind == SBLAS_K_ROWSPLIT) &&
+            rows >= 2 * SBLAS_PIECE_ROWS) {
+            k = (int)(rows / SBLAS_PIECE_ROWS);
+            if (k > SBLAS_PIECE_MAX) k = SBLAS_PIECE_MAX;
+        }
+        npiece += k;
+    }
+    if (D->nev_unit < 2 * npiece) {
+        cudaEvent_t *ev = (cudaEvent_t *)calloc((size_t)2 * npiece, sizeof(cudaEvent_t));
         if (!ev) return 1;
         for (int i = 0; i < D->nev_unit; ++i) ev[i] = D->ev_unit[i];
         free(D->ev_unit);
         D->ev_unit = ev;
-        for (int i = D->nev_unit; i < 2 * nu; ++i) CU(cudaEventCreateWithFlags(&D->ev_unit[i], cudaEventDisableTiming));
-        D->nev_unit = 2 * nu;
+        for (int i = D->nev_unit; i < 2 * npiece; ++i) CU(cudaEventCreateWithFlags(&D->ev_unit[i], cudaEventDisableTiming));
+        D->nev_unit = 2 * npiece;
+    }
+    if (P->cap_pieces < npiece) {
+        free(P->piece_lo); free(P->piece_hi); free(P->piece_unit);
+        P->piece_lo = (int *)malloc((size_t)npiece * sizeof(int));
+        P->piece_hi = (int *)malloc((size_t)npiece * sizeof(int));
+        P->piece_unit = (int *)malloc((size_t)npiece * sizeof(int));
+        if (!P->piece_lo || !P->piece_hi || !P->piece_unit) { P->cap_pieces = 0; return 1; }
+        P->cap_pieces = npiece;
+    }
+    int np = 0;
+    for (int u = 0; u < nu; ++u) {
+        const sblas_unit *U = &P->units[S->unit_begin + u];
+        const long long rows = (long long)U->args.row_hi - U->args.row_lo + 1;
+        int k = 1;
+        if ((U->kind == SBLAS_K_SHORT || U->kind == SBLAS_K_ROWTILE || U->kind == SBLAS_K_ROWSPLIT) &&
+            rows >= 2 * SBLAS_PIECE_ROWS) {
+            k = (int)(rows / SBLAS_PIECE_ROWS);
+            if (k > SBLAS_PIECE_MAX) k = SBLAS_PIECE_MAX;
+        }
+        for (int i = 0; i < k; ++i) {
+            /* cuts on multiples of 64 rows: whole tiles of the row-tile kernel for every R */
+            long long lo = U->args.row_lo + (rows * i / k) / 64 * 64, hi = U->args.row_lo + (rows * (i + 1) / k) / 64 * 64 - 1;
+            if (i == 0) lo = U->args.row_lo;
+            if (i == k - 1) hi = U->args.row_hi;
+            P->piece_lo[np] = (int)lo; P->piece_hi[np] = (int)hi; P->piece_unit[np] = S->unit_begin + u;
+            ++np;
+        }
     }
     cudaStream_t st = D->streams[0], cs = D->copy_stream;
+    const int skip = owned_skip(P, 0);                  /* a split first row belongs to the previous rank */
+    const int exchange = P->rank_mode && P->world > 1 && P->peer_bound;
     if (x && D->col_hi >= D->col_lo)
         CU(cudaMemcpyAsync(D->d_x + D->col_lo, x + D->col_lo, (size_t)(D->col_hi - D->col_lo + 1) * sizeof(double),
                            cudaMemcpyHostToDevice, st));
-    /* uploads: panel 0 on the compute stream, the others on the copy stream */
-    for (int u = 0; u < nu && beta != 0.0; ++u) {
-        const sblas_seg_args *a = &P->units[S->unit_begin + u].args;
-        const long long rows = (long long)a->row_hi - a->row_lo + 1;
+    /* uploads: piece 0 on the compute stream, the others on the copy stream */
+    for (int p = 0; p < np && beta != 0.0; ++p) {
+        const long long rows = (long long)P->piece_hi[p] - P->piece_lo[p] + 1;
         if (rows <= 0) continue;
-        CU(cudaMemcpyAsync(D->d_y + a->row_lo, y + D->first_row + a->row_lo, (size_t)rows * sizeof(double),
-                           cudaMemcpyHostToDevice, u == 0 ? st : cs));
-        if (u > 0) CU(cudaEventRecord(D->ev_unit[2 * u], cs));
+        CU(cudaMemcpyAsync(D->d_y + P->piece_lo[p], y + D->first_row + P->piece_lo[p], (size_t)rows * sizeof(double),
+                           cudaMemcpyHostToDevice, p == 0 ? st : cs));
+        if (p > 0) CU(cudaEventRecord(D->ev_unit[2 * p], cs));
     }
-    for (int u = 0; u < nu; ++u) {
-        sblas_unit *U = &P->units[S->unit_begin + u];
-        const sblas_seg_args *a = &U->args;
-        const long long rows = (long long)a->row_hi - a->row_lo + 1;
-        if (u > 0 && beta != 0.0 && rows > 0) CU(cudaStreamWaitEvent(st, D->ev_unit[2 * u], 0));
+    for (int p = 0; p < np; ++p) {
+        sblas_unit *U = &P->units[P->piece_unit[p]];
+        const long long rows = (long long)P->piece_hi[p] - P->piece_lo[p] + 1;
+        if (p > 0 && beta != 0.0 && rows > 0) CU(cudaStreamWaitEvent(st, D->ev_unit[2 * p], 0));
         U->args.alpha = alpha; U->args.beta = beta;
         U->args.edge = S->args.edge;
-        CU(sblas_launch_spmv_segment(&U->args, U->kind, U->ipt, 0, st));
+        if (exchange)
+            U->args.edge = P->my_base + (long long)((P->epoch + 1) & 1ull) * P->table_words +
+                           (long long)P->rank * (2 * P->max_local) + 2 * S->lidx;
+        sblas_seg_args a = U->args;
+        a.row_lo = P->piece_lo[p]; a.row_hi = P->piece_hi[p];
+        CU(sblas_launch_spmv_segment(&a, U->kind, U->ipt, 0, st));
         if (rows <= 0) continue;
-        if (u + 1 < nu) {                          /* comes down while the next panel computes */
-            CU(cudaEventRecord(D->ev_unit[2 * u + 1], st));
-            CU(cudaStreamWaitEvent(cs, D->ev_unit[2 * u + 1], 0));
-            CU(cudaMemcpyAsync(y + D->first_row + a->row_lo, D->d_y + a->row_lo, (size_t)rows * sizeof(double),
-                               cudaMemcpyDeviceToHost, cs));
+        long long lo = P->piece_lo[p], cnt = rows;
+        if (lo == 0 && skip) { lo = 1; cnt -= 1; }
+        if (p + 1 < np) {                          /* comes down while the next piece computes */
+            CU(cudaEventRecord(D->ev_unit[2 * p + 1], st));
+            CU(cudaStreamWaitEvent(cs, D->ev_unit[2 * p + 1], 0));
+            if (cnt > 0)
+                CU(cudaMemcpyAsync(y + D->first_row + lo, D->d_y + lo, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, cs));
         } else {
-            CU(cudaMemcpyAsync(y + D->first_row + a->row_lo, D->d_y + a->row_lo, (size_t)rows * sizeof(double),
-                               cudaMemcpyDeviceToHost, st));
+            if (exchange) CU(sblas_spmv_plan_exchange_merge(P, alpha, beta));
+            else if (D->nmerge > 0) CU(enqueue_merge(P, 0, alpha, beta));
+            if (cnt > 0)
+                CU(cudaMemcpyAsync(y + D->first_row + lo, D->d_y + lo, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
         }
     }
     CU(cudaEventRecord(D->ev_done, st));
@@ -1025,12 +1098,16 @@ fail:
 int sblas_spmv_plan_execute(sblas_spmv_plan *P, const double *alpha, const double *x, const double *beta, double *y)
 {
     int rc;
-    if (!P->dry && P->ndev == 1 && P->nseg == 1 && P->devs[0].seg_begin >= 0 && P->devs[0].nmerge == 0 &&
-        P->devs[0].nstreams == 1 && (!P->rank_mode || P->world == 1) && x && y &&
-        P->segs[0].unit_end - P->segs[0].unit_begin >= 2 && env_int("SBLAS_PIPELINE", 1))
+    if (!P->dry && P->ndev == 1 && P->nseg == 1 && P->devs[0].seg_begin >= 0 && P->devs[0].nstreams == 1 && x && y &&
+        (!P->rank_mode || P->world == 1 || P->peer_bound) && (P->rank_mode || P->devs[0].nmerge == 0) &&
+        env_int("SBLAS_PIPELINE", 1))
         return execute_pipelined(P, *alpha, x, *beta, y);
     if ((rc = sblas_spmv_plan_upload(P, x, *beta != 0.0 ? y : NULL)) != 0) return rc;
     if ((rc = sblas_spmv_plan_execute_device(P, *alpha, *beta, 0)) != 0) return rc;
+    /* one rank of a multi-process job with bound peer tables: the split-row exchange is part of the
+     * product (P2P publish + merge kernels on the same stream); every rank must make this call */
+    if (P->rank_mode && P->world > 1 && P->peer_bound &&
+        (rc = sblas_spmv_plan_exchange_merge(P, *alpha, *beta)) != 0) return rc;
     return sblas_spmv_plan_download(P, y);
 }
 

@@ -74,6 +74,8 @@ struct __align__(128) Stage {
 constexpr int kRing = 4;                       /* partial-sum buffers / named-barrier ids: a warp is at most
                                                   kStages tiles ahead of the slowest one, so 4 slots suffice */
 static_assert(kGroups * kRing < 16, "named barrier ids");
+static_assert(kStages < kRing, "a warp may run kStages tiles ahead: the partial-sum ring / barrier ids need one more slot");
+static_assert((kRing & (kRing - 1)) == 0, "ring index is masked");
 constexpr int kRedDoubles = kRing * (2 + 3) * kCWarps;          /* per group */
 constexpr int kBarBytes = 2 * kStages * 8;                      /* full[], empty[] mbarriers */
 constexpr int kSmemBytes = kStages * (int)sizeof(Stage) + kBarBytes + kGroups * kRedDoubles * 8;

@@ -80,7 +80,48 @@ __global__ void fill_uniform_kernel(double *p, long long count, uint64_t seed, d
     for (; i < count; i += stride) p[i] = lo + (hi - lo) * u01(mix64(seed ^ (uint64_t)i * 0x2545F4914F6CDD1Dull));
 }
 
+/* read-only streaming probe: 8 independent 16-byte loads in flight per thread */
+__global__ void __launch_bounds__(256) read_probe_kernel(const int4 *__restrict__ p, size_t n16, int *out)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    int acc = 0;
+    for (; i + 7 * stride < n16; i += 8 * stride) {
+        int4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(v[k].x), "=r"(v[k].y), "=r"(v[k].z), "=r"(v[k].w) : "l"(p + i + k * stride));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc += v[k].x ^ v[k].y ^ v[k].z ^ v[k].w;
+    }
+    if (acc == 0x7fffffff) out[0] = acc;
+}
+
 }  // namespace
+
+extern "C" double sblas_synth_read_probe(const void *d_buf, unsigned long long bytes, int reps, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    int *d_out = NULL;
+    if (bytes < (1ull << 20) || cudaMalloc((void **)&d_out, sizeof(int)) != cudaSuccess) return -1.0;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = -1.0;
+    for (int r = 0; r < reps + 1; ++r) {                         /* first pass = warm-up */
+        cudaEventRecord(e0, st);
+        read_probe_kernel<<<148 * 16, 256, 0, st>>>((const int4 *)d_buf, (size_t)(bytes / 16), d_out);
+        cudaEventRecord(e1, st);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const size_t n16 = (size_t)(bytes / 16), stride = (size_t)148 * 16 * 256;
+        const double read = (double)(n16 / (8 * stride)) * (8 * stride) * 16.0;     /* bytes the loop really touches */
+        if (r > 0 && ms > 0.f && read / ms / 1e6 > best) best = read / ms / 1e6;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    return best;
+}
 
 extern "C" int sblas_synth_fill_csr(const long long *d_rowptr, int row_first, int nrows, long long k0, long long k1,
                                     int n, int cols_mode, long long band, unsigned long long seed, int value_mode,

@@ -148,3 +148,13 @@ def test_ingest_matches_the_compiled_reference_loader_live(tmp_path):
             got = loader(path)
             assert got[0:2] == want[0:2] and got[5] == want[5]
             assert (got[2] == want[2]).all() and (got[3] == want[3]).all() and (got[4] == want[4]).all()
+
+
+def test_symmetric_file_must_be_square(tmp_path):
+    """A file that declares itself symmetric with n > m would mirror entries into rows that do not exist:
+    rejected with its own code (-7) instead of writing past the row pointer."""
+    path = str(tmp_path / "rect_sym.mtx")
+    with open(path, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real symmetric\n3 9 2\n1 8 1.5\n3 9 2.5\n")
+    with pytest.raises(IOError, match="-7"):
+        sb.mtx_read_csr(path)

@@ -44,6 +44,10 @@ def run_all_versions(rp, col, val, x, alpha, beta, y0, ngpu_list=(1,), kernels=(
 
 
 def gpu_counts():
+    """GPU counts the in-process entry points are driven with.  SBLAS_EXPECT_GPUS=N makes a lease with
+    fewer visible GPUs an error instead of a silently smaller sweep (the multi-GPU CI leg sets it)."""
+    want = int(os.environ.get("SBLAS_EXPECT_GPUS", "0"))
+    assert ngpus() >= want, "SBLAS_EXPECT_GPUS=%d but only %d GPU(s) visible" % (want, ngpus())
     return [g for g in (1, 2, 4, 8) if g <= ngpus()]
 
 
@@ -176,8 +180,6 @@ def test_row_tile_kernel_on_medium_panels(monkeypatch):
     run_all_versions(rp, col, val, x, -1.75, 0.625, y0, (1,), kernels=(1,), what="row tiles off")
 
 
-@pytest.mark.skipif(os.environ.get("SBLAS_TEST_ROWSPLIT") != "1",
-                    reason="row-split kernel is opt-in this round (SBLAS_MEDIUM bit 1); set SBLAS_TEST_ROWSPLIT=1 to run (passes)")
 def test_row_split_kernel_on_long_medium_panels(monkeypatch):
     """Panels whose longest row lies in (256, 2048] and whose rows are mostly that long go to the row-split
     kernel, G = 2 / 4 / 8 warps per row (SBLAS_MEDIUM bit 1).  One block per G, with empty and short rows
