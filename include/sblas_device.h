@@ -90,20 +90,31 @@ cudaError_t sblas_launch_edge_merge(const int *mrow, const int *mbeg, const doub
 
 /* Fused split-row exchange for one-process-per-GPU plans over peer-mapped (symmetric)
  * memory, no host involvement and no NCCL call per product:
- *   publish: copy this rank's outgoing partials straight into the OWNER ranks' tables over
- *            NVLink (P2P stores), fence, then raise the owner's arrive flag (epoch counter);
- *            waits for the owner's ack of epoch-2 first (tables are double buffered by parity)
- *   merge:   spin until every contributing rank's arrive flag reached `epoch`, finish the
+ *   publish: advance the product counter *epoch_ctr (device memory, so that a product is the same
+ *            launch sequence every time: CUDA-graph replay); copy this rank's partials (local_edge,
+ *            nlocal = edge slots) into its own table half `epoch & 1` and the outgoing ones straight into
+ *            the OWNER ranks' tables over NVLink (P2P stores), fence, then raise the owners' arrive flags
+ *            (epoch counters); waits for the owners' ack of epoch-2 first (tables are double buffered)
+ *   merge:   spin until every contributing rank's arrive flag reached *epoch_ctr, finish the
  *            split rows from the local table in ascending segment order, ack the contributors.
  * Buffer layout of every rank (8-byte words): table[2][table_words], arrive[world], ack[world]. */
-cudaError_t sblas_launch_edge_publish(const double *local_block, const int *out_slot, const int *out_owner,
+cudaError_t sblas_launch_edge_publish(const double *local_edge, int nlocal, const int *out_slot, const int *out_owner,
                                       const long long *out_off, int nout, const int *owners, int nowners,
                                       void *const *peer_bases, long long table_words, int world, int my_rank,
-                                      unsigned long long epoch, cudaStream_t s);
+                                      unsigned long long *epoch_ctr, cudaStream_t s);
 cudaError_t sblas_launch_edge_merge_wait(const int *mrow, const int *mbeg, const long long *msrc_off, int nmerge,
                                          double *y, double alpha, double beta, const int *contrib, int ncontrib,
                                          void *const *peer_bases, long long table_words, int world, int my_rank,
-                                         unsigned long long epoch, cudaStream_t s);
+                                         const unsigned long long *epoch_ctr, cudaStream_t s);
+
+/* x <- y across the ranks of a one-process-per-GPU job over peer-mapped memory: every rank
+ * stores the `count` rows of y it owns (y_src) into every rank's x at [dst_off, dst_off + count) -- an all-gather
+ * with P2P stores over NVLink --, fenced by two rounds of epoch flags (ready: all ranks have finished reading
+ * x; written: all slices have landed).  peer_x[r] / peer_flags[r] (2*world 8-byte words, zeroed) are rank r's
+ * buffers as mapped in this process; chain_ctr is a device counter owned by the plan. */
+cudaError_t sblas_launch_chain_gather(const double *y_src, long long count, long long dst_off, void *const *peer_x,
+                                      void *const *peer_flags, int world, int my_rank, unsigned long long *chain_ctr,
+                                      cudaStream_t s);
 
 /* device fill helpers used by the plan */
 cudaError_t sblas_launch_fill_f64(double *p, long long n, double v, cudaStream_t s);

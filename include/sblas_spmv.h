@@ -129,10 +129,23 @@ int sblas_spmv_plan_download(sblas_spmv_plan *plan, double *y);
  * Square matrices; in-process plans (or a single-rank plan).  Follow with execute_device. */
 int sblas_spmv_plan_chain(sblas_spmv_plan *plan);
 
+/* One-process-per-GPU form of the chain: bind peer-mapped x buffers (n doubles each; peer_x[r] / peer_flags[r] =
+ * rank r's x and flag buffer -- 2*world zeroed 8-byte words -- as mapped in this process, e.g. from
+ * torch.distributed._symmetric_memory).  The plan then computes on peer_x[rank], and sblas_spmv_plan_chain
+ * all-gathers the y rows every rank owns into EVERY rank's x with P2P stores over NVLink, fenced by epoch flags
+ * (no NCCL call, no host synchronisation); every rank must call it once per product. */
+int sblas_spmv_plan_bind_peer_x(sblas_spmv_plan *plan, void *const *peer_x, void *const *peer_flags);
+
 /* Device-resident execute: x and y already sit in the plan's device buffers
  * (see sblas_spmv_plan_x / _y); nothing crosses PCIe.  Enqueues on the plan's
  * streams and returns without synchronising unless sync != 0. */
 int sblas_spmv_plan_execute_device(sblas_spmv_plan *plan, double alpha, double beta, int sync);
+
+/* One product with x and y resident, the iterative-use entry point: the segments'
+ * kernels plus, for a rank plan with bound peer tables, the fused split-row exchange -- captured into a
+ * CUDA graph on single-GPU plans and replayed (one cudaGraphLaunch per product; re-captured when alpha or
+ * beta change; SBLAS_GRAPH=0 disables).  Asynchronous on the plan's stream. */
+int sblas_spmv_plan_step(sblas_spmv_plan *plan, double alpha, double beta);
 
 /* accessors (dev = index of the GPU inside the plan, 0 for a rank plan) */
 int sblas_spmv_plan_num_devices(const sblas_spmv_plan *plan);

@@ -82,6 +82,13 @@ def lib():
         L.oracle_synth_fill_csr.restype = None
         L.oracle_synth_fill_uniform.argtypes = [_pd, _LL, C.c_ulonglong, C.c_double, C.c_double]
         L.oracle_synth_fill_uniform.restype = None
+        L.oracle_csrmm.argtypes = [C.c_int, C.c_int, _pi, _pi, _pd, _pd, _LL, _pd, _LL, C.c_double, C.c_double]
+        L.oracle_csrmm.restype = None
+        L.oracle_csrmm_bound.argtypes = [C.c_int, C.c_int, _pi, _pi, _pd, _pd, _LL, _pd, _LL, C.c_double, C.c_double, _pd]
+        L.oracle_csrmm_bound.restype = None
+        L.oracle_spmm_mgpu.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, _pi, _pi, _pd, C.c_double, _pd, _pd, C.c_int]
+        L.oracle_csr2csc.argtypes = [C.c_int, C.c_int, C.c_int, _pi, _pi, _pd, _pi, _pi, _pd]
+        L.oracle_csr2csc.restype = None
         _lib = L
     return _lib
 
@@ -127,6 +134,93 @@ def synth_fill_uniform(count, seed, lo=0.0, hi=1.0):
     out = np.empty(count, np.float64)
     lib().oracle_synth_fill_uniform(out, int(count), int(seed), lo, hi)
     return out
+
+
+def csrmm(rowptr32, col, val, B, alpha, beta, C, ngpu=None):
+    """C_out = alpha*A*B + beta*C (oracle_csrmm), B (k x n) and C (m x n) column-major, i.e. numpy arrays of
+    shape (n, k) / (n, m) in C order or Fortran-ordered (k, n) / (m, n).  ngpu: go through the column split of the
+    reference's entry point (oracle_spmm_mgpu).  Returns a new array shaped like C."""
+    rp = _c(rowptr32, np.int32)
+    m = len(rp) - 1
+    Bf, Cf = np.asfortranarray(B, dtype=np.float64), np.asfortranarray(C, dtype=np.float64).copy(order="F")
+    k, n = Bf.shape
+    assert Cf.shape == (m, n)
+    bflat, cflat = Bf.reshape(-1, order="F"), Cf.reshape(-1, order="F")
+    if ngpu is None:
+        lib().oracle_csrmm(m, n, rp, _c(col, np.int32), _c(val, np.float64), bflat, k, cflat, m, alpha, beta)
+    else:
+        assert lib().oracle_spmm_mgpu(m, n, k, alpha, rp, _c(col, np.int32), _c(val, np.float64), beta, bflat, cflat, ngpu) == 0
+    return cflat.reshape((m, n), order="F")
+
+
+def csrmm_bound(rowptr32, col, val, B, alpha, beta, C):
+    rp = _c(rowptr32, np.int32)
+    m = len(rp) - 1
+    Bf, Cf = np.asfortranarray(B, dtype=np.float64), np.asfortranarray(C, dtype=np.float64)
+    k, n = Bf.shape
+    out = np.empty(m * n)
+    lib().oracle_csrmm_bound(m, n, rp, _c(col, np.int32), _c(val, np.float64), Bf.reshape(-1, order="F"), k,
+                             Cf.reshape(-1, order="F"), m, alpha, beta, out)
+    return out.reshape((m, n), order="F")
+
+
+def csr2csc(m, n, rowptr32, col, val):
+    """CSR -> CSC like the reference's host transposition (oracle_csr2csc).  Returns (colptr, rowidx, val)."""
+    rp, cc, vv = _c(rowptr32, np.int32), _c(col, np.int32), _c(val, np.float64)
+    nnz = int(rp[-1])
+    colptr, rowidx, out = np.zeros(n + 1, np.int32), np.zeros(max(nnz, 1), np.int32), np.zeros(max(nnz, 1), np.float64)
+    lib().oracle_csr2csc(m, n, nnz, rp, cc if nnz else np.zeros(1, np.int32), vv if nnz else np.zeros(1), rowidx, colptr, out)
+    return colptr, rowidx[:nnz], out[:nnz]
+
+
+def ref_sptrans():
+    """The reference's OWN host transposition (sptrans/sptrans_v1/src/tranpose.h, compiled where it lies behind
+    oracle/ref_sptrans_shim.cpp into oracle/_ref/libref_sptrans.so), or None.  Pure host code: runs without a GPU.
+    Returns f(m, n, rowptr32, col, val) -> (colptr, rowidx, val)."""
+    p = os.path.join(_HERE, "_ref", "libref_sptrans.so")
+    if not os.path.exists(p):
+        return None
+    R = C.CDLL(p)
+    R.ref_matrix_transposition.argtypes = [C.c_int, C.c_int, C.c_int, _pi, _pi, _pd, _pi, _pi, _pd]
+    R.ref_matrix_transposition.restype = None
+
+    def call(m, n, rowptr32, col, val):
+        rp, cc, vv = _c(rowptr32, np.int32), _c(col, np.int32), _c(val, np.float64)
+        nnz = int(rp[-1])
+        colptr, rowidx, out = np.zeros(n + 1, np.int32), np.zeros(max(nnz, 1), np.int32), np.zeros(max(nnz, 1), np.float64)
+        R.ref_matrix_transposition(m, n, nnz, rp, cc if nnz else np.zeros(1, np.int32), vv if nnz else np.zeros(1), rowidx, colptr, out)
+        return colptr, rowidx[:nnz], out[:nnz]
+    return call
+
+
+_ref_spmm = None
+
+
+def ref_spmm():
+    """The reference's OWN SpMM entry points (spmm/src/dspmm_mgpu_baseline.cu, unmodified, compiled where it
+    lies with oracle/compat_csrmv.h mapping cusparseDcsrmm onto cusparseSpMM) from
+    oracle/_ref/libref_spmm.so, or None.  GPU only.  Returns f(m, n, k, alpha, nnz, rowptr32, col, val, beta,
+    B_flat, C_flat, ngpu, omp) -> status; C_flat (column-major) is updated in place."""
+    global _ref_spmm
+    if _ref_spmm is not None:
+        return _ref_spmm
+    p = os.path.join(_HERE, "_ref", "libref_spmm.so")
+    if not os.path.exists(p):
+        return None
+    R = C.CDLL(p)
+    vp = C.c_void_p
+    at = [C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int]
+    f = getattr(R, "_Z19cusparse_mgpu_csrmmiiiPKdiPiS1_PdS0_S2_S2_i")
+    fo = getattr(R, "_Z23cusparse_mgpu_csrmm_ompiiiPKdiPiS1_PdS0_S2_S2_i")
+    f.argtypes = at
+    fo.argtypes = at
+
+    def call(m, n, k, alpha, nnz, rp, col, val, beta, B, Cm, ngpu, omp=True):
+        a, b = C.c_double(alpha), C.c_double(beta)
+        return (fo if omp else f)(m, n, k, C.addressof(a), nnz, rp.ctypes.data, col.ctypes.data, val.ctypes.data,
+                                  C.addressof(b), B.ctypes.data, Cm.ctypes.data, ngpu)
+    _ref_spmm = call
+    return call
 
 
 _ref = None

@@ -3,7 +3,8 @@
  * The reference's three entry points (spmv/src/dspmv_mgpu_baseline.cu:163,
  * dspmv_mgpu_v1.cu:200,206, dspmv_mgpu_v2.cu:351,357) call the legacy cuSPARSE routines
  * cusparseDcsrmv / cusparseDcsrmv_mp, which were removed in CUDA 11.  This header, force-included
- * with `nvcc -include oracle/compat_csrmv.h`, supplies those two names on top of the generic API
+ * with `nvcc -include oracle/compat_csrmv.h`, supplies those two names (and cusparseDcsrmm, which the
+ * reference's SpMM calls, spmm/src/dspmm_mgpu_baseline.cu:225,450) on top of the generic API
  * that replaced them (cusparseSpMV, CUSPARSE_SPMV_CSR_ALG1 for csrmv and _ALG2 -- the
  * load-balanced "merge path" algorithm -- for csrmv_mp), so that the UNMODIFIED reference sources
  * compile where they lie into oracle/_ref/libref_spmv.so (oracle/Makefile, target refspmv).
@@ -74,5 +75,42 @@ static inline cusparseStatus_t cusparseDcsrmv_mp(cusparseHandle_t handle, cuspar
 {
     return sblas_compat_csrmv(handle, transA, m, n, nnz, alpha, descrA, csrVal, csrRowPtr, csrColInd, x, beta, y,
                               CUSPARSE_SPMV_CSR_ALG2);
+}
+
+/* cusparseDcsrmm (spmm/src/dspmm_mgpu_baseline.cu:225-241, :450-466): C = alpha*op(A)*B + beta*C, A CSR,
+ * B (k x n, ld ldb) and C (m x n, ld ldc) column-major -> cusparseSpMM, default algorithm. */
+static inline cusparseStatus_t cusparseDcsrmm(cusparseHandle_t handle, cusparseOperation_t transA, int m, int n, int k,
+                                              int nnz, const double *alpha, const cusparseMatDescr_t descrA,
+                                              const double *csrVal, const int *csrRowPtr, const int *csrColInd,
+                                              const double *B, int ldb, const double *beta, double *C, int ldc)
+{
+    (void)descrA;
+    cusparseSpMatDescr_t A = NULL;
+    cusparseDnMatDescr_t mB = NULL, mC = NULL;
+    cusparseStatus_t st;
+    cudaStream_t s = 0;
+    void *buf = NULL;
+    size_t need = 0;
+    if (m == 0 || n == 0) return CUSPARSE_STATUS_SUCCESS;
+    st = cusparseGetStream(handle, &s);
+    if (st != CUSPARSE_STATUS_SUCCESS) return st;
+    st = cusparseCreateCsr(&A, m, k, nnz, (void *)csrRowPtr, (void *)csrColInd, (void *)csrVal, CUSPARSE_INDEX_32I,
+                           CUSPARSE_INDEX_32I, CUSPARSE_INDEX_BASE_ZERO, CUDA_R_64F);
+    if (st != CUSPARSE_STATUS_SUCCESS) return st;
+    st = cusparseCreateDnMat(&mB, k, n, ldb, (void *)B, CUDA_R_64F, CUSPARSE_ORDER_COL);
+    if (st == CUSPARSE_STATUS_SUCCESS) st = cusparseCreateDnMat(&mC, m, n, ldc, (void *)C, CUDA_R_64F, CUSPARSE_ORDER_COL);
+    if (st == CUSPARSE_STATUS_SUCCESS)
+        st = cusparseSpMM_bufferSize(handle, transA, CUSPARSE_OPERATION_NON_TRANSPOSE, alpha, A, mB, beta, mC, CUDA_R_64F,
+                                     CUSPARSE_SPMM_ALG_DEFAULT, &need);
+    if (st == CUSPARSE_STATUS_SUCCESS && need > 0 && cudaMalloc(&buf, need) != cudaSuccess) st = CUSPARSE_STATUS_ALLOC_FAILED;
+    if (st == CUSPARSE_STATUS_SUCCESS)
+        st = cusparseSpMM(handle, transA, CUSPARSE_OPERATION_NON_TRANSPOSE, alpha, A, mB, beta, mC, CUDA_R_64F,
+                          CUSPARSE_SPMM_ALG_DEFAULT, buf);
+    cudaStreamSynchronize(s);
+    if (buf) cudaFree(buf);
+    if (mC) cusparseDestroyDnMat(mC);
+    if (mB) cusparseDestroyDnMat(mB);
+    if (A) cusparseDestroySpMat(A);
+    return st;
 }
 #endif

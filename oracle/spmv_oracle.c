@@ -546,3 +546,80 @@ void oracle_synth_fill_uniform(double *p, ll count, unsigned long long seed, dou
     for (ll i = 0; i < count; ++i)
         p[i] = lo + (hi - lo) * o_u01(o_mix64(seed ^ (unsigned long long)i * 0x2545F4914F6CDD1Dull));
 }
+
+/* ------------------------------------------------------------------------- */
+/* SpMM.  The arithmetic of cusparseDcsrmm as the reference calls it
+ * (spmm/src/dspmm_mgpu_baseline.cu:225-241, :450-466): C = alpha*A*B + beta*C, A CSR with an int32 row
+ * pointer (base 0), B (k x n, leading dimension ldb) and C (m x n, ldc) dense COLUMN-major; every
+ * C(i,c) summed left to right over row i.  Columns in parallel over the host cores. */
+void oracle_csrmm(int m, int n, const int *rowptr, const int *col, const double *val, const double *B, ll ldb,
+                  double *C, ll ldc, double alpha, double beta)
+{
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+    for (int c = 0; c < n; ++c) {
+        const double *b = B + (ll)c * ldb;
+        double *out = C + (ll)c * ldc;
+        for (int i = 0; i < m; ++i) {
+            double s = 0.0;
+            for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) s += val[k] * b[col[k]];
+            out[i] = alpha * s + beta * out[i];
+        }
+    }
+}
+
+/* bound(i,c) = |alpha| sum_j |a_ij||b_jc| + |beta||c_ic|: the denominator of the per-entry tolerance */
+void oracle_csrmm_bound(int m, int n, const int *rowptr, const int *col, const double *val, const double *B, ll ldb,
+                        const double *C_in, ll ldc, double alpha, double beta, double *bound)
+{
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+    for (int c = 0; c < n; ++c) {
+        const double *b = B + (ll)c * ldb;
+        for (int i = 0; i < m; ++i) {
+            double s = 0.0;
+            for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) s += fabs(val[k]) * fabs(b[col[k]]);
+            bound[(ll)c * m + i] = fabs(alpha) * s + fabs(beta) * fabs(C_in[(ll)c * ldc + i]);
+        }
+    }
+}
+
+/* the whole entry point, cusparse_mgpu_csrmm[_omp] (dspmm_mgpu_baseline.cu:83-280, :282-524): columns of B
+ * and C split over the GPUs, dev_n[d] = floor((d+1)n/ngpu) - floor(dn/ngpu), offsets floor(dn/ngpu)*k and *m
+ * (:338-342; C int arithmetic, the floor() of an int is a no-op), one csrmm per GPU on its slice */
+int oracle_spmm_mgpu(int m, int n, int k, double alpha, const int *rowptr, const int *col, const double *val,
+                     double beta, const double *B, double *C, int ngpu)
+{
+    if (ngpu <= 0) return -1;
+    for (int d = 0; d < ngpu; ++d) {
+        const int c0 = (int)((ll)d * n / ngpu), c1 = (int)((ll)(d + 1) * n / ngpu);
+        oracle_csrmm(m, c1 - c0, rowptr, col, val, B + (ll)c0 * k, k, C + (ll)c0 * m, m, alpha, beta);
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* sparse transposition CSR -> CSC, restating the reference's host routine
+ * sptrans/sptrans_v1/src/tranpose.h:3-40 (matrix_transposition): histogram of the column indices,
+ * exclusive scan (utils.h:312-329), then the rows in order, every entry appended to its column -- so a
+ * column keeps the CSR order of its entries (rows ascending, duplicates in input order). */
+void oracle_csr2csc(int m, int n, int nnz, const int *csrRowPtr, const int *csrColIdx, const double *csrVal,
+                    int *cscRowIdx, int *cscColPtr, double *cscVal)
+{
+    memset(cscColPtr, 0, sizeof(int) * ((size_t)n + 1));
+    for (int i = 0; i < nnz; ++i) cscColPtr[csrColIdx[i]]++;
+    int run = 0;                                        /* in-place exclusive scan over n + 1 entries */
+    for (int c = 0; c <= n; ++c) { const int t = cscColPtr[c]; cscColPtr[c] = run; run += t; }
+    int *incr = (int *)malloc(sizeof(int) * ((size_t)n + 1));
+    memcpy(incr, cscColPtr, sizeof(int) * ((size_t)n + 1));
+    for (int row = 0; row < m; ++row)
+        for (int j = csrRowPtr[row]; j < csrRowPtr[row + 1]; ++j) {
+            const int c = csrColIdx[j];
+            cscRowIdx[incr[c]] = row;
+            cscVal[incr[c]] = csrVal[j];
+            incr[c]++;
+        }
+    free(incr);
+}

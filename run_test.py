@@ -1,14 +1,16 @@
 #!/usr/bin/env python3
-"""run_test.py -- Python 3 port of the SpMV half of the reference driver (run_test.py:1-66,
-179-186 of pnnl/s-blas; the original is Python 2 and also drives spmm/sptrsv/sptrans, which
-are outside this repo's path).  Same behaviour for SpMV: for every matrix in matrices.txt
-and every GPU count 1..n_gpus it runs
+"""run_test.py -- Python 3 port of what the reference driver actually runs (run_test.py:179-186 of
+pnnl/s-blas calls test_spmv() and test_spmm(); the original is Python 2 and also carries disabled
+sptrsv/sptrans halves, which are outside this repo's path).  For every matrix in matrices.txt and every
+GPU count 1..n_gpus it runs
 
-    ./test_spmv f <mtxpath><matrix> <gpu> 1 1 f
+    ./test_spmv f <mtxpath><matrix> <gpu> 1 1 f          (run_test.py:45-66)
+    ./test_spmm <mtxpath><matrix> 128 <gpu> 1            (run_test.py:160-175)
 
-scrapes the `m:` and `Average` lines exactly like parse_spmv (run_test.py:29-43) and writes
-results.csv with the labels V1/V2/V3 = baseline/v1/v2.  Extra columns (gflops, alg_gbs) are appended
-after the reference's eight so existing readers keep working.
+scrapes the `m:` / `Average` lines exactly like parse_spmv (run_test.py:29-43) and the `Matrix A --` /
+`Matrix B --` / `SPMM:` lines like parse_spmm (run_test.py:146-159) and writes results.csv with the
+reference's columns (V1/V2/V3 = baseline/v1/v2 for spmv).  Extra columns (gflops, alg_gbs) are appended
+after the reference's so existing readers keep working.
 """
 import os
 import subprocess
@@ -71,6 +73,40 @@ def test_spmv(mtxlist, result_file):
     result_file.write("\n")
 
 
+def parse_spmm(result):
+    """run_test.py:146-159, token for token."""
+    m = n = k = nnz = 0
+    v1_time = float("nan")
+    for line in result.strip().split("\n"):
+        l = line.strip()
+        if l.startswith("Matrix A --"):
+            words = l.strip("\n").split(" ")
+            m = int(words[4])
+            n = int(words[6])
+            nnz = int(words[8])
+        if l.startswith("Matrix B --"):
+            words = l.strip("\n").split(" ")
+            k = int(words[6])
+        if l.startswith("SPMM:"):
+            words = l.strip("\n").split(" ")
+            v1_time = float(words[5])
+    return m, n, k, nnz, v1_time
+
+
+def test_spmm(mtxlist, result_file):
+    result_file.write("kernel, matrix, n_gpu, m, n, k, nnz, version, time, gflops\n")
+    for mtx in mtxlist:
+        for gpu in range(1, n_gpus + 1):
+            cmd = "./test_spmm " + mtxpath + mtx + " 128 " + str(gpu) + " 1 "
+            print(cmd)
+            result = subprocess.run(cmd, shell=True, capture_output=True, text=True, cwd=HERE).stdout
+            m, n, k, nnz, v1_time = parse_spmm(result)
+            ok = v1_time == v1_time and v1_time > 0
+            result_file.write("spmm, %s, %d, %d, %d, %d, %d, V1, %s, %s\n" % (
+                mtx, gpu, m, n, k, nnz, v1_time, (2.0 * nnz * k / v1_time / 1e9) if ok else "nan"))
+    result_file.write("\n")
+
+
 def main():
     listing = os.path.join(HERE, "matrices.txt")
     mtxlist = [l.strip() for l in open(listing)] if os.path.exists(listing) else ["qh768.mtx"]
@@ -80,6 +116,7 @@ def main():
     ensure_sample_matrix()
     with open(os.path.join(HERE, "results.csv"), "w") as fh:
         test_spmv(mtxlist, fh)
+        test_spmm(mtxlist, fh)
 
 
 if __name__ == "__main__":

@@ -84,6 +84,8 @@ def lib():
     L.sblas_spmv_plan_upload.argtypes = [_vp, _vp, _vp]
     L.sblas_spmv_plan_download.argtypes = [_vp, _vp]
     L.sblas_spmv_plan_execute_device.argtypes = [_vp, C.c_double, C.c_double, C.c_int]
+    L.sblas_spmv_plan_step.argtypes = [_vp, C.c_double, C.c_double]
+    L.sblas_spmv_plan_bind_peer_x.argtypes = [_vp, P(_vp), P(_vp)]
     L.sblas_spmv_plan_num_devices.argtypes = [_vp]
     L.sblas_spmv_plan_num_segments.argtypes = [_vp]
     L.sblas_spmv_plan_segment.argtypes = [_vp, C.c_int, P(Part), P(C.c_int)]
@@ -133,6 +135,21 @@ def lib():
     L.sblas_synth_fill_csr.argtypes = [_vp, C.c_int, C.c_int, _LL, _LL, C.c_int, C.c_int, _LL, C.c_ulonglong,
                                        C.c_int, C.c_double, _vp, _vp, _vp]
     L.sblas_synth_fill_uniform.argtypes = [_vp, _LL, C.c_ulonglong, C.c_double, C.c_double, _vp]
+    sm = [C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]
+    for name in ("sblas_spmm_mgpu", "cusparse_mgpu_csrmm", "cusparse_mgpu_csrmm_omp"):
+        getattr(L, name).argtypes = sm
+    L.sblas_spmm_plan_create.argtypes = [P(_vp), C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int]
+    L.sblas_spmm_plan_execute.argtypes = [_vp, C.c_int, P(C.c_double), _vp, P(C.c_double), _vp]
+    L.sblas_spmm_plan_execute_device.argtypes = [_vp, C.c_int, C.c_int, C.c_double, _vp, C.c_double, _vp, C.c_int]
+    L.sblas_spmm_plan_columns.argtypes = [_vp, C.c_int, C.c_int, P(C.c_int), P(C.c_int)]
+    L.sblas_spmm_plan_stream.argtypes = [_vp, C.c_int]
+    L.sblas_spmm_plan_stream.restype = _vp
+    L.sblas_spmm_plan_num_devices.argtypes = [_vp]
+    L.sblas_spmm_plan_destroy.argtypes = [_vp]
+    L.sblas_spmm_plan_destroy.restype = None
+    L.sblas_sptrans_mgpu.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]
+    L.kernal_sptrans.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    L.sblas_sptrans_last_device_ms.restype = C.c_double
     L.sblas_synth_read_probe.argtypes = [_vp, C.c_ulonglong, C.c_int, _vp]
     L.sblas_synth_read_probe.restype = C.c_double
     _lib = L
@@ -304,6 +321,13 @@ class Plan:
         if rc != 0:
             raise RuntimeError("sblas_spmv_plan_execute_device rc=%d: %s" % (rc, last_error()))
 
+    def step(self, alpha, beta):
+        """One product with x and y resident (kernels + fused split-row exchange of a bound rank plan); replayed
+        from a CUDA graph on single-GPU plans.  Asynchronous on the plan's stream."""
+        rc = lib().sblas_spmv_plan_step(self._h, alpha, beta)
+        if rc != 0:
+            raise RuntimeError("sblas_spmv_plan_step rc=%d: %s" % (rc, last_error()))
+
     def x_window(self, dev=0):
         """[first, last] column the GPU's shard references (what upload() copies of x)."""
         a, b = _LL(), _LL()
@@ -315,6 +339,15 @@ class Plan:
         rc = lib().sblas_spmv_plan_chain(self._h)
         if rc != 0:
             raise RuntimeError("chain failed: %s" % last_error())
+
+    def bind_peer_x(self, peer_x_ptrs, peer_flag_ptrs):
+        """Rank plans: compute on the peer-mapped x buffer peer_x_ptrs[rank]; chain() then all-gathers y into every
+        rank's x over NVLink (peer_flag_ptrs[r]: rank r's 2*world zeroed 8-byte words)."""
+        a = (_vp * len(peer_x_ptrs))(*[int(p) for p in peer_x_ptrs])
+        b = (_vp * len(peer_flag_ptrs))(*[int(p) for p in peer_flag_ptrs])
+        rc = lib().sblas_spmv_plan_bind_peer_x(self._h, a, b)
+        if rc != 0:
+            raise RuntimeError("sblas_spmv_plan_bind_peer_x rc=%d: %s" % (rc, last_error()))
 
     def merge_gathered(self, gathered_ptr, alpha, beta):
         rc = lib().sblas_spmv_plan_merge_gathered(self._h, int(gathered_ptr), alpha, beta)
@@ -480,3 +513,89 @@ def synth_fill_uniform(d_p, count, seed, lo=0.0, hi=1.0, stream=None):
 def synth_read_probe(d_buf, nbytes, reps=3, stream=None):
     """Read-only HBM bandwidth (GB/s) of a streaming-load kernel over nbytes of device memory."""
     return lib().sblas_synth_read_probe(int(d_buf), int(nbytes), int(reps), stream)
+
+
+# ----------------------------------------------------------------------------- SpMM (SURVEY.md section 8f-2)
+def _colmajor(a, rows, cols, name):
+    """B / C as the reference holds them: column-major.  Accepts a Fortran-ordered (rows, cols) array or a flat
+    array of rows*cols doubles; returns the flat view (no copy)."""
+    a = np.asarray(a)
+    if a.dtype != np.float64:
+        raise TypeError(name + " must be float64")
+    if a.ndim == 2:
+        if a.shape != (rows, cols) or not a.flags["F_CONTIGUOUS"]:
+            raise TypeError("%s must be a Fortran-ordered (%d, %d) array (column-major, like the reference's buffers)" % (name, rows, cols))
+        return a.reshape(-1, order="F")
+    if a.size != rows * cols or not a.flags["C_CONTIGUOUS"]:
+        raise TypeError(name + " must hold rows*cols contiguous doubles")
+    return a
+
+
+def cusparse_mgpu_csrmm(m, n, k, alpha, nnz_A, csrRowPtr_A, csrColIndex_A, csrVal_A, beta, B_dense, C_dense, ngpu, omp=False):
+    """spmm/include/spmm_kernel.h:6-31 (omp=True: the _omp entry point).  C_dense is updated in place."""
+    a, b = C.c_double(alpha), C.c_double(beta)
+    fn = lib().cusparse_mgpu_csrmm_omp if omp else lib().cusparse_mgpu_csrmm
+    Bf, Cf = _colmajor(B_dense, k, n, "B_dense"), _colmajor(C_dense, m, n, "C_dense")
+    return fn(m, n, k, C.addressof(a), nnz_A, _ptr(_host(csrRowPtr_A, np.int32, "csrRowPtr_A")),
+              _ptr(_host(csrColIndex_A, np.int32, "csrColIndex_A")), _ptr(_host(csrVal_A, np.float64, "csrVal_A")),
+              C.addressof(b), _ptr(Bf), _ptr(Cf), ngpu)
+
+
+class SpmmPlan:
+    """A resident on every GPU of the plan (include/sblas_spmm.h)."""
+
+    def __init__(self, m, k, nnz, rowptr32, col, val, ngpu):
+        h = _vp()
+        rc = lib().sblas_spmm_plan_create(C.byref(h), m, k, nnz, _ptr(_host(rowptr32, np.int32, "csrRowPtr_A")),
+                                          _ptr(_host(col, np.int32, "csrColIndex_A")), _ptr(_host(val, np.float64, "csrVal_A")), ngpu)
+        if rc != 0:
+            raise RuntimeError("sblas_spmm_plan_create rc=%d: %s" % (rc, last_error()))
+        self._h, self.m, self.k, self.ngpu = h, m, k, ngpu
+
+    def execute(self, n, alpha, B, beta, Cm):
+        a, b = C.c_double(alpha), C.c_double(beta)
+        rc = lib().sblas_spmm_plan_execute(self._h, n, C.byref(a), _ptr(_colmajor(B, self.k, n, "B")), C.byref(b),
+                                           _ptr(_colmajor(Cm, self.m, n, "C")))
+        if rc != 0:
+            raise RuntimeError("sblas_spmm_plan_execute rc=%d: %s" % (rc, last_error()))
+
+    def execute_device(self, dev, nd, alpha, d_B, beta, d_C, sync=False):
+        rc = lib().sblas_spmm_plan_execute_device(self._h, dev, nd, alpha, int(d_B), beta, int(d_C), 1 if sync else 0)
+        if rc != 0:
+            raise RuntimeError("sblas_spmm_plan_execute_device rc=%d: %s" % (rc, last_error()))
+
+    def columns(self, n, dev):
+        a, b = C.c_int(), C.c_int()
+        assert lib().sblas_spmm_plan_columns(self._h, n, dev, C.byref(a), C.byref(b)) == 0
+        return a.value, b.value
+
+    def stream(self, dev=0):
+        return lib().sblas_spmm_plan_stream(self._h, dev)
+
+    def destroy(self):
+        if self._h:
+            lib().sblas_spmm_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+# ----------------------------------------------------------------------------- transposition (SURVEY.md section 8f-4)
+def kernal_sptrans(m, n, nnz, ngpu, csrRowPtr, csrColIdx, csrVal, ref=None):
+    """CSR -> CSC on ngpu GPUs (sptrans/sptrans_v1/src/sptrans_kernal.h:80, the reference's entry point).
+    Returns (status, cscColPtr, cscRowIdx, cscVal); ref = (colptr, rowidx, val) host arrays to be compared like the
+    reference's *_ref arguments (status 2 on a mismatch)."""
+    rp, cc, vv = _host(csrRowPtr, np.int32, "csrRowPtr"), _host(csrColIdx, np.int32, "csrColIdx"), _host(csrVal, np.float64, "csrVal")
+    colptr, rowidx, val = np.zeros(n + 1, np.int32), np.zeros(max(nnz, 1), np.int32), np.zeros(max(nnz, 1), np.float64)
+    r = [None, None, None] if ref is None else [_ptr(_host(ref[1], np.int32, "ref rowidx")), _ptr(_host(ref[0], np.int32, "ref colptr")),
+                                                _ptr(_host(ref[2], np.float64, "ref val"))]
+    rc = lib().kernal_sptrans(m, n, nnz, ngpu, _ptr(rp), _ptr(cc), _ptr(vv), _ptr(rowidx), _ptr(colptr), _ptr(val), *r)
+    return rc, colptr, rowidx[:nnz], val[:nnz]
+
+
+def sptrans_last_device_ms():
+    return lib().sblas_sptrans_last_device_ms()

@@ -30,6 +30,7 @@ typedef struct sblas_dev {
     int first_row, last_row, rows, nnz;
     double *d_val; int *d_col; int own_matrix;
     int *d_rowptr; double *d_x; double *d_y;
+    long long *stage64;               /* plan build: the int64 row pointer slice on its way to d_rowptr */
     double *d_edge; int edge_is_host, edge_bound; void *h_edge_alloc;
     double *d_carry, *d_tail; int *d_tstart, *d_tmeta;
     /* merge lists of the split rows this GPU owns */
@@ -62,7 +63,11 @@ struct sblas_spmv_plan {
     int cap_pieces; int *piece_lo, *piece_hi, *piece_unit;    /* pieces of the pipelined host execute */
     /* fused exchange over peer-mapped memory */
     int peer_bound, nout, nowners, ncontrib;
-    unsigned long long epoch;
+    unsigned long long *d_epoch;     /* product counter of the fused exchange, advanced by the publish kernel */
+    /* x <- y across ranks over peer-mapped memory (sblas_spmv_plan_bind_peer_x) */
+    int peer_x_bound; void **d_peer_x, **d_peer_xflags; unsigned long long *d_chain_ctr; double *x_alloc;
+    /* CUDA-graph replay of one product (sblas_spmv_plan_step) */
+    void *graph_exec; int graph_valid, graph_warm, capturing; double graph_alpha, graph_beta;
     long long table_words;
     double *my_base;
     void **d_peer_bases; int *d_out_slot, *d_out_owner, *d_owners, *d_contrib; long long *d_out_off, *d_msrc_off;

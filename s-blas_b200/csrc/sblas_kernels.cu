@@ -528,26 +528,41 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-/* one thread: the lists are a handful of entries (<= 2 per local segment) */
-__global__ void edge_publish_kernel(const double *local_block, const int *out_slot, const int *out_owner,
+/* One warp.  The product counter (epoch) lives in device memory and is advanced HERE, so that a
+ * product -- segments, publish, merge -- is the same launch sequence every time (CUDA-graph replay).
+ *   1. epoch = ++*epoch_ctr; back-pressure: every owner must have consumed what was written two products ago
+ *   2. this rank's own partials (local_edge, nlocal = edge slots) go into its half `epoch & 1` of its OWN table
+ *   3. the outgoing ones go straight into the OWNER ranks' tables over NVLink (P2P stores)
+ *   4. fence, then raise the owners' arrive flags to `epoch` */
+__global__ void edge_publish_kernel(const double *local_edge, int nlocal, const int *out_slot, const int *out_owner,
                                     const long long *out_off, int nout, const int *owners, int nowners,
                                     void *const *peer_bases, long long table_words, int world, int my_rank,
-                                    unsigned long long epoch)
+                                    unsigned long long *epoch_ctr)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int parity = (int)(epoch & 1ull);
+    if (blockIdx.x != 0) return;
+    __shared__ unsigned long long s_epoch;
     unsigned long long *mine = reinterpret_cast<unsigned long long *>(peer_bases[my_rank]);
-    for (int k = 0; k < nowners; ++k) {
-        /* back-pressure: the owner must have consumed what we wrote two products ago */
-        const unsigned long long *ack = mine + 2 * table_words + world + owners[k];
-        while (ld_acquire_sys(ack) + 2ull < epoch) { }
+    if (threadIdx.x == 0) {
+        const unsigned long long e = *epoch_ctr + 1ull;
+        *epoch_ctr = e;
+        s_epoch = e;
+        for (int k = 0; k < nowners; ++k) {
+            const unsigned long long *ack = mine + 2 * table_words + world + owners[k];
+            while (ld_acquire_sys(ack) + 2ull < e) { }
+        }
     }
-    for (int i = 0; i < nout; ++i) {
+    __syncthreads();
+    const unsigned long long epoch = s_epoch;
+    const int parity = (int)(epoch & 1ull);
+    double *own = reinterpret_cast<double *>(mine) + parity * table_words + (long long)my_rank * nlocal;
+    for (int i = threadIdx.x; i < nlocal; i += blockDim.x) own[i] = local_edge[i];
+    for (int i = threadIdx.x; i < nout; i += blockDim.x) {
         double *dst = reinterpret_cast<double *>(peer_bases[out_owner[i]]) + parity * table_words + out_off[i];
-        *reinterpret_cast<volatile double *>(dst) = *reinterpret_cast<const volatile double *>(local_block + out_slot[i]);
+        *reinterpret_cast<volatile double *>(dst) = local_edge[out_slot[i]];
     }
     __threadfence_system();
-    for (int k = 0; k < nowners; ++k) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < nowners; k += blockDim.x) {
         unsigned long long *flag = reinterpret_cast<unsigned long long *>(peer_bases[owners[k]]) + 2 * table_words + my_rank;
         st_release_sys(flag, epoch);
     }
@@ -556,9 +571,10 @@ __global__ void edge_publish_kernel(const double *local_block, const int *out_sl
 __global__ void edge_merge_wait_kernel(const int *__restrict__ mrow, const int *__restrict__ mbeg,
                                        const long long *__restrict__ msrc_off, int nmerge, double *y, double alpha,
                                        double beta, const int *contrib, int ncontrib, void *const *peer_bases,
-                                       long long table_words, int world, int my_rank, unsigned long long epoch)
+                                       long long table_words, int world, int my_rank, const unsigned long long *epoch_ctr)
 {
     unsigned long long *mine = reinterpret_cast<unsigned long long *>(peer_bases[my_rank]);
+    const unsigned long long epoch = *epoch_ctr;              /* advanced by this product's publish kernel */
     if (threadIdx.x == 0) {
         for (int k = 0; k < ncontrib; ++k) {
             const unsigned long long *flag = mine + 2 * table_words + contrib[k];
@@ -583,6 +599,50 @@ __global__ void edge_merge_wait_kernel(const int *__restrict__ mrow, const int *
             st_release_sys(ack, epoch);
         }
     }
+}
+
+/* ---- x <- y across the ranks of a one-process-per-GPU job, over peer-mapped memory:
+ * an all-gather of the y rows each rank owns into EVERY rank's replica of x, with two rounds of flags
+ *   ready:   "I have finished reading x for this product" -- nobody's x may be overwritten before all are ready
+ *   written: "my rows are in your x"                       -- the next product starts when all have written
+ * flags buffer of every rank (8-byte words): ready[world], written[world]; the counter lives on the device so
+ * that the sequence is the same every product. */
+__global__ void chain_ready_kernel(void *const *peer_flags, int world, int my_rank, unsigned long long *chain_ctr)
+{
+    if (blockIdx.x != 0) return;
+    __shared__ unsigned long long s_e;
+    if (threadIdx.x == 0) { const unsigned long long e = *chain_ctr + 1ull; *chain_ctr = e; s_e = e; }
+    __syncthreads();
+    const unsigned long long e = s_e;
+    __threadfence_system();
+    for (int p = threadIdx.x; p < world; p += blockDim.x)
+        st_release_sys(reinterpret_cast<unsigned long long *>(peer_flags[p]) + my_rank, e);
+    const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(peer_flags[my_rank]);
+    for (int p = threadIdx.x; p < world; p += blockDim.x)
+        while (ld_acquire_sys(mine + p) < e) { }
+}
+
+__global__ void __launch_bounds__(256) chain_copy_kernel(const double *__restrict__ y_src, long long count, long long dst_off,
+                                                         void *const *peer_x, int world)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (int p = 0; p < world; ++p) {
+        double *dst = reinterpret_cast<double *>(peer_x[p]) + dst_off;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) dst[i] = y_src[i];
+    }
+    __threadfence_system();
+}
+
+__global__ void chain_done_kernel(void *const *peer_flags, int world, int my_rank, const unsigned long long *chain_ctr)
+{
+    if (blockIdx.x != 0) return;
+    const unsigned long long e = *chain_ctr;
+    __threadfence_system();
+    for (int p = threadIdx.x; p < world; p += blockDim.x)
+        st_release_sys(reinterpret_cast<unsigned long long *>(peer_flags[p]) + world + my_rank, e);
+    const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(peer_flags[my_rank]);
+    for (int p = threadIdx.x; p < world; p += blockDim.x)
+        while (ld_acquire_sys(mine + world + p) < e) { }
 }
 
 __global__ void fill_f64_kernel(double *p, long long n, double v)
@@ -692,14 +752,14 @@ extern "C" cudaError_t sblas_launch_edge_merge(const int *mrow, const int *mbeg,
     return cudaGetLastError();
 }
 
-extern "C" cudaError_t sblas_launch_edge_publish(const double *local_block, const int *out_slot, const int *out_owner,
-                                                 const long long *out_off, int nout, const int *owners, int nowners,
-                                                 void *const *peer_bases, long long table_words, int world,
-                                                 int my_rank, unsigned long long epoch, cudaStream_t s)
+extern "C" cudaError_t sblas_launch_edge_publish(const double *local_edge, int nlocal, const int *out_slot,
+                                                 const int *out_owner, const long long *out_off, int nout,
+                                                 const int *owners, int nowners, void *const *peer_bases,
+                                                 long long table_words, int world, int my_rank,
+                                                 unsigned long long *epoch_ctr, cudaStream_t s)
 {
-    if (nout <= 0) return cudaSuccess;
-    edge_publish_kernel<<<1, 32, 0, s>>>(local_block, out_slot, out_owner, out_off, nout, owners, nowners, peer_bases,
-                                         table_words, world, my_rank, epoch);
+    edge_publish_kernel<<<1, 32, 0, s>>>(local_edge, nlocal, out_slot, out_owner, out_off, nout, owners, nowners,
+                                         peer_bases, table_words, world, my_rank, epoch_ctr);
     return cudaGetLastError();
 }
 
@@ -707,11 +767,25 @@ extern "C" cudaError_t sblas_launch_edge_merge_wait(const int *mrow, const int *
                                                     int nmerge, double *y, double alpha, double beta,
                                                     const int *contrib, int ncontrib, void *const *peer_bases,
                                                     long long table_words, int world, int my_rank,
-                                                    unsigned long long epoch, cudaStream_t s)
+                                                    const unsigned long long *epoch_ctr, cudaStream_t s)
 {
     if (nmerge <= 0 && ncontrib <= 0) return cudaSuccess;
     edge_merge_wait_kernel<<<1, 128, 0, s>>>(mrow, mbeg, msrc_off, nmerge, y, alpha, beta, contrib, ncontrib,
-                                             peer_bases, table_words, world, my_rank, epoch);
+                                             peer_bases, table_words, world, my_rank, epoch_ctr);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t sblas_launch_chain_gather(const double *y_src, long long count, long long dst_off,
+                                                 void *const *peer_x, void *const *peer_flags, int world, int my_rank,
+                                                 unsigned long long *chain_ctr, cudaStream_t s)
+{
+    chain_ready_kernel<<<1, 32, 0, s>>>(peer_flags, world, my_rank, chain_ctr);
+    if (count > 0) {
+        long long blocks = (count + 255) / 256;
+        if (blocks > 148 * 4) blocks = 148 * 4;
+        chain_copy_kernel<<<(unsigned)blocks, 256, 0, s>>>(y_src, count, dst_off, peer_x, world);
+    }
+    chain_done_kernel<<<1, 32, 0, s>>>(peer_flags, world, my_rank, chain_ctr);
     return cudaGetLastError();
 }
 

@@ -134,11 +134,15 @@ static void free_dev(sblas_dev *D, int dry)
 void sblas_spmv_plan_destroy(sblas_spmv_plan *P)
 {
     if (!P) return;
+    if (P->x_alloc) { P->devs[0].d_x = P->x_alloc; P->x_alloc = NULL; }   /* the bound peer x is the caller's: free our own */
     for (int d = 0; d < P->ndev; ++d) free_dev(&P->devs[d], P->dry);
     if (P->peer_bound) {
         cudaFree(P->d_peer_bases); cudaFree(P->d_out_slot); cudaFree(P->d_out_owner); cudaFree(P->d_out_off);
-        cudaFree(P->d_owners); cudaFree(P->d_contrib); cudaFree(P->d_msrc_off);
+        cudaFree(P->d_owners); cudaFree(P->d_contrib); cudaFree(P->d_msrc_off); cudaFree(P->d_epoch);
     }
+    if (P->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)P->graph_exec);
+    if (P->d_peer_x) { cudaFree(P->d_peer_x); cudaFree(P->d_peer_xflags); cudaFree(P->d_chain_ctr); }
+
     free(P->devs); free(P->segs); free(P->units); free(P->parts); free(P->g_owner); free(P->g_local);
     free(P->g_lo); free(P->g_hi); free(P->g_sf); free(P->g_sl);
     free(P->piece_lo); free(P->piece_hi); free(P->piece_unit);
@@ -314,7 +318,6 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
                       const int *devices, int src_flags)
 {
     int rc = 0;
-    long long *stage64 = NULL;
     int *d_stats = NULL, *h_stats = NULL, stats_cap = 0;      /* row-block statistics scratch */
     int *d_mm = NULL;                                         /* column range scratch */
     const int dry = (src_flags & SBLAS_LAYOUT_ONLY) != 0;     /* host layout only: no CUDA call at all */
@@ -428,11 +431,22 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
         CU(cudaMalloc((void **)&D->d_x, (size_t)(P->n > 0 ? P->n : 1) * sizeof(double)));
         CU(cudaMalloc((void **)&D->d_y, (size_t)(D->rows > 0 ? D->rows : 1) * sizeof(double)));
         /* int64 host row pointer slice -> int32 rebased/clamped, on the GPU */
-        CU(cudaMalloc((void **)&stage64, (size_t)(D->rows + 1) * sizeof(long long)));
-        CU(cudaMemcpyAsync(stage64, rp + D->first_row, (size_t)(D->rows + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
-        CU(sblas_launch_rebase_rowptr(stage64, D->first_idx, D->nnz, (long long)D->rows + 1, D->d_rowptr, st));
+        CU(cudaMalloc((void **)&D->stage64, (size_t)(D->rows + 1) * sizeof(long long)));
+        CU(cudaMemcpyAsync(D->stage64, rp + D->first_row, (size_t)(D->rows + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+        CU(sblas_launch_rebase_rowptr(D->stage64, D->first_idx, D->nnz, (long long)D->rows + 1, D->d_rowptr, st));
+        }   /* !dry */
+    }
+
+    /* ---- second pass per GPU (the uploads of ALL GPUs are in flight by now, each over its own PCIe link):
+     * wait for this GPU's shard, then column window, panels, tile metadata */
+    for (int d = 0; d < ndev; ++d) {
+        sblas_dev *D = &P->devs[d];
+        if (D->seg_begin < 0) continue;
+        if (!dry) {
+        CU(cudaSetDevice(D->device));
+        cudaStream_t st = D->streams[0];
         CU(cudaStreamSynchronize(st));
-        CU(cudaFree(stage64)); stage64 = NULL;
+        CU(cudaFree(D->stage64)); D->stage64 = NULL;
 
         /* the window of x this shard reads: [col_lo, col_hi] (one reduction over col at plan time) */
         D->col_lo = 0; D->col_hi = P->n - 1;
@@ -458,7 +472,7 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
         const int panels_on = !dry && P->kernel == 1 && D->kind == SBLAS_K_TMA && !getenv("SBLAS_KIND") &&
                               env_int("SBLAS_PANELS", 1) != 0;
         const int short_max = env_int("SBLAS_SHORT_MAX", 4);
-        const int medium_on = env_int("SBLAS_MEDIUM", 1);
+        const int medium_on = env_int("SBLAS_MEDIUM", 3);       /* bit 0: row-tile panels, bit 1: row-split panels */
         const long long panel_min_nnz = env_int("SBLAS_PANEL_MIN_NNZ", 1 << 20);
         long long tiles_total = 0;
         for (int s = D->seg_begin; s < D->seg_end; ++s) {
@@ -668,7 +682,7 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
     }
     return 0;
 fail:
-    if (stage64) cudaFree(stage64);
+    for (int d = 0; d < P->ndev; ++d) if (P->devs[d].stage64) { cudaFree(P->devs[d].stage64); P->devs[d].stage64 = NULL; }
     if (d_stats) cudaFree(d_stats);
     if (d_mm) cudaFree(d_mm);
     free(h_stats);
@@ -766,9 +780,6 @@ static int enqueue_segments(sblas_spmv_plan *P, int d, double alpha, double beta
     for (int s = D->seg_begin; s < D->seg_end; ++s) {
         sblas_seg *S = &P->segs[s];
         S->args.alpha = alpha; S->args.beta = beta;
-        if (P->peer_bound)       /* edges go straight into this product's half of the exchange table */
-            S->args.edge = P->my_base + (long long)((P->epoch + 1) & 1ull) * P->table_words +
-                           (long long)P->rank * (2 * P->max_local) + 2 * S->lidx;
         for (int ui = S->unit_begin; ui < S->unit_end; ++ui) {
             sblas_unit *U = &P->units[ui];
             U->args.alpha = alpha; U->args.beta = beta;
@@ -942,8 +953,21 @@ static int owned_skip(const sblas_spmv_plan *P, int d)
 int sblas_spmv_plan_chain(sblas_spmv_plan *P)
 {
     int rc = 0;
+    if (!P->dry && P->m == P->n && P->rank_mode && P->world > 1 && P->peer_x_bound) {
+        /* one process per GPU: all-gather of the owned y rows into every rank's x with P2P stores + flags */
+        sblas_dev *D = &P->devs[0];
+        CU(cudaSetDevice(D->device));
+        int skip = 0;
+        long long cnt = 0;
+        if (D->seg_begin >= 0) { skip = owned_skip(P, 0); cnt = (long long)D->rows - skip; }
+        CU(sblas_launch_chain_gather(D->seg_begin >= 0 ? D->d_y + skip : NULL, cnt > 0 ? cnt : 0,
+                                     D->seg_begin >= 0 ? (long long)D->first_row + skip : 0, (void *const *)P->d_peer_x,
+                                     (void *const *)P->d_peer_xflags, P->world, P->rank, P->d_chain_ctr,
+                                     D->streams ? D->streams[0] : 0));
+        return 0;
+    }
     if (P->dry || P->m != P->n || (P->rank_mode && P->world > 1)) {
-        sblas_set_error("%s%s (line %d)", "chain needs a square matrix and every shard in this process", "", __LINE__);
+        sblas_set_error("%s%s (line %d)", "chain needs a square matrix and every shard in this process (or bound peer x buffers)", "", __LINE__);
         return -1;
     }
     const int nd = P->ndev;
@@ -1067,9 +1091,6 @@ static int execute_pipelined(sblas_spmv_plan *P, double alpha, const double *x, 
         if (p > 0 && beta != 0.0 && rows > 0) CU(cudaStreamWaitEvent(st, D->ev_unit[2 * p], 0));
         U->args.alpha = alpha; U->args.beta = beta;
         U->args.edge = S->args.edge;
-        if (exchange)
-            U->args.edge = P->my_base + (long long)((P->epoch + 1) & 1ull) * P->table_words +
-                           (long long)P->rank * (2 * P->max_local) + 2 * S->lidx;
         sblas_seg_args a = U->args;
         a.row_lo = P->piece_lo[p]; a.row_hi = P->piece_hi[p];
         CU(sblas_launch_spmv_segment(&a, U->kind, U->ipt, 0, st));
@@ -1215,6 +1236,8 @@ int sblas_spmv_plan_bind_peer_tables(sblas_spmv_plan *P, void *const *peer_bases
         CU(cudaMalloc((void **)&P->d_owners, (size_t)(nown + 1) * sizeof(int)));
         CU(cudaMalloc((void **)&P->d_contrib, (size_t)(ncon + 1) * sizeof(int)));
         CU(cudaMalloc((void **)&P->d_msrc_off, (size_t)(D->nmsrc + 1) * sizeof(long long)));
+        CU(cudaMalloc((void **)&P->d_epoch, sizeof(unsigned long long)));
+        CU(cudaMemset(P->d_epoch, 0, sizeof(unsigned long long)));
         CU(cudaMemcpy(P->d_out_slot, out_slot, (size_t)nout * sizeof(int), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(P->d_out_owner, out_owner, (size_t)nout * sizeof(int), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(P->d_out_off, out_off, (size_t)nout * sizeof(long long), cudaMemcpyHostToDevice));
@@ -1227,7 +1250,7 @@ int sblas_spmv_plan_bind_peer_tables(sblas_spmv_plan *P, void *const *peer_bases
     P->my_base = (double *)peer_bases[P->rank];
     P->table_words = table_words;
     P->peer_bound = 1;
-    P->epoch = 0;
+    P->graph_valid = 0;
 fail:
     free(out_slot); free(out_owner); free(out_off); free(owners); free(contrib); free(seen);
     return rc;
@@ -1248,18 +1271,102 @@ int sblas_spmv_plan_exchange_merge_phase(sblas_spmv_plan *P, double alpha, doubl
     if (!P->peer_bound) return -1;
     sblas_dev *D = &P->devs[0];
     CU(cudaSetDevice(D->device));
-    if (phase != 2) P->epoch += 1;
     const int slots = 2 * P->max_local;
-    const double *local_block = P->my_base + (long long)(P->epoch & 1ull) * P->table_words + (long long)P->rank * slots;
     cudaStream_t st = D->streams ? D->streams[0] : 0;
+    /* publish always runs: it advances the product counter the merge reads */
     if (phase != 2)
-    CU(sblas_launch_edge_publish(local_block, P->d_out_slot, P->d_out_owner, P->d_out_off, P->nout, P->d_owners,
-                                 P->nowners, (void *const *)P->d_peer_bases, P->table_words, P->world, P->rank,
-                                 P->epoch, st));
+        CU(sblas_launch_edge_publish(D->d_edge, slots, P->d_out_slot, P->d_out_owner, P->d_out_off, P->nout, P->d_owners,
+                                     P->nowners, (void *const *)P->d_peer_bases, P->table_words, P->world, P->rank,
+                                     P->d_epoch, st));
     if (D->seg_begin >= 0 && phase != 1)
         CU(sblas_launch_edge_merge_wait(D->d_mrow, D->d_mbeg, P->d_msrc_off, D->nmerge, D->d_y, alpha, beta,
                                         P->d_contrib, P->ncontrib, (void *const *)P->d_peer_bases, P->table_words,
-                                        P->world, P->rank, P->epoch, st));
+                                        P->world, P->rank, P->d_epoch, st));
+fail:
+    return rc;
+}
+
+/* One product on a resident plan, x and y on the device: the segments' kernels and, for a rank plan
+ * with bound peer tables, the split-row exchange.  On single-GPU plans (one rank of a multi-process job
+ * or a one-GPU plan) the launch sequence is captured into a CUDA graph the second time it runs with the
+ * same alpha / beta and REPLAYED from then on: one cudaGraphLaunch per product.
+ * SBLAS_GRAPH=0 keeps plain stream launches. */
+int sblas_spmv_plan_step(sblas_spmv_plan *P, double alpha, double beta)
+{
+    int rc = 0;
+    const int exchange = P->rank_mode && P->world > 1 && P->peer_bound;
+    const int graphable = !P->dry && P->ndev == 1 && P->devs[0].seg_begin >= 0 && P->devs[0].nstreams == 1 &&
+                          (P->rank_mode ? (P->world == 1 || exchange) : P->devs[0].nmerge >= 0) && env_int("SBLAS_GRAPH", 1);
+    if (!graphable) {
+        if ((rc = sblas_spmv_plan_execute_device(P, alpha, beta, 0)) != 0) return rc;
+        if (exchange) rc = sblas_spmv_plan_exchange_merge(P, alpha, beta);
+        return rc;
+    }
+    sblas_dev *D = &P->devs[0];
+    cudaStream_t st = D->streams[0];
+    CU(cudaSetDevice(D->device));
+    if (P->graph_valid && P->graph_alpha == alpha && P->graph_beta == beta) {
+        CU(cudaGraphLaunch((cudaGraphExec_t)P->graph_exec, st));
+        return 0;
+    }
+    if (!P->graph_warm) {               /* first product: plain launches (one-time attribute set-up happens here) */
+        P->graph_warm = 1;
+        if ((rc = sblas_spmv_plan_execute_device(P, alpha, beta, 0)) != 0) return rc;
+        if (exchange) rc = sblas_spmv_plan_exchange_merge(P, alpha, beta);
+        return rc;
+    }
+    if (P->graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)P->graph_exec); P->graph_exec = NULL; P->graph_valid = 0; }
+    {
+        cudaGraph_t g = NULL;
+        CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        P->capturing = 1;
+        rc = sblas_spmv_plan_execute_device(P, alpha, beta, 0);
+        if (rc == 0 && exchange) rc = sblas_spmv_plan_exchange_merge(P, alpha, beta);
+        P->capturing = 0;
+        cudaError_t e = cudaStreamEndCapture(st, &g);
+        if (rc != 0 || e != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            if (rc == 0) { sblas_set_error("%s%s (line %d)", "graph capture failed: ", cudaGetErrorString(e), __LINE__); rc = 1; }
+            return rc;
+        }
+        cudaGraphExec_t ge = NULL;
+        e = cudaGraphInstantiate(&ge, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { sblas_set_error("%s%s (line %d)", "cudaGraphInstantiate: ", cudaGetErrorString(e), __LINE__); return 1; }
+        P->graph_exec = (void *)ge;
+        P->graph_alpha = alpha; P->graph_beta = beta; P->graph_valid = 1;
+        CU(cudaGraphLaunch(ge, st));
+    }
+fail:
+    return rc;
+}
+
+/* Rank plans, iterative use: make every rank's x a peer-mapped buffer (n doubles; e.g. symmetric memory) so that
+ * sblas_spmv_plan_chain can all-gather y into it over NVLink.  peer_x[r] / peer_flags[r] (2*world 8-byte words,
+ * zeroed) = rank r's buffers as mapped in THIS process.  The plan computes on peer_x[rank] from now on. */
+int sblas_spmv_plan_bind_peer_x(sblas_spmv_plan *P, void *const *peer_x, void *const *peer_flags)
+{
+    int rc = 0;
+    if (!P->rank_mode || P->dry || !peer_x || !peer_flags) return -1;
+    sblas_dev *D = &P->devs[0];
+    CU(cudaSetDevice(D->device >= 0 ? D->device : 0));
+    if (!P->d_peer_x) {
+        CU(cudaMalloc((void **)&P->d_peer_x, (size_t)P->world * sizeof(void *)));
+        CU(cudaMalloc((void **)&P->d_peer_xflags, (size_t)P->world * sizeof(void *)));
+        CU(cudaMalloc((void **)&P->d_chain_ctr, sizeof(unsigned long long)));
+        CU(cudaMemset(P->d_chain_ctr, 0, sizeof(unsigned long long)));
+    }
+    CU(cudaMemcpy(P->d_peer_x, peer_x, (size_t)P->world * sizeof(void *), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(P->d_peer_xflags, peer_flags, (size_t)P->world * sizeof(void *), cudaMemcpyHostToDevice));
+    if (D->seg_begin >= 0) {
+        if (!P->x_alloc) P->x_alloc = D->d_x;                 /* still freed with the plan */
+        D->d_x = (double *)peer_x[P->rank];
+        for (int s = 0; s < P->nseg; ++s) P->segs[s].args.x = D->d_x;
+        for (int u = 0; u < P->nunits; ++u) P->units[u].args.x = D->d_x;
+    }
+    P->peer_x_bound = 1;
+    P->graph_valid = 0;
 fail:
     return rc;
 }

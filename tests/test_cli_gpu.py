@@ -134,3 +134,26 @@ def test_run_test_py3_driver(tmp_path):
     for r, label in zip(rows, ("V1", "V2", "V3")):
         f = [c.strip() for c in r.split(",")]
         assert f[:7] == ["spmv", "qh768.mtx", "1", "768", "768", "2934", label] and float(f[7]) > 0
+
+
+def test_spmm_cli_contract(qh768, tmp_path):
+    """test_spmm: the reference's argv and the three lines run_test.py scrapes (run_test.py:146-175), the PASS
+    line of the multi-GPU vs single-GPU comparison (spmm/test/dspmm_baseline_test.cu:540-545)."""
+    import torch
+    sys.path.insert(0, ROOT)
+    import run_test
+    mtx = str(tmp_path / "qh768.mtx")
+    write_mtx(mtx, qh768)
+    cli = os.path.join(ROOT, "test_spmm")
+    for ngpu in [g for g in (1, 2, 4, 8) if g <= torch.cuda.device_count()]:
+        rc, out = run([cli, mtx, "128", str(ngpu), "1"])
+        assert rc == 0, out
+        lines = out.strip().split("\n")
+        assert lines[0] == "Using %d GPU(s)." % ngpu
+        assert "Matrix A -- #row: 768 #col: 768 nnz: 2934" in lines
+        assert "Matrix B -- #row: 768 #col: 128 (dense)" in lines
+        assert "mgpu check: PASS" in lines
+        m, n, k, nnz, t = run_test.parse_spmm(out)
+        assert (m, n, k, nnz) == (768, 768, 128, 2934) and t > 0
+    rc, out = run([cli, mtx, "128"])
+    assert rc != 0 and out.startswith("Usage: ./spmm")

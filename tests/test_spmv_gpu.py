@@ -508,3 +508,111 @@ def test_upload_moves_only_the_columns_a_shard_reads():
         p.execute(A, x, B, y)
         check_tol(y, oracle.csr_spmv(rp, col, val, x, A, B, y0), oracle.csr_spmv_bound(rp, col, val, x, A, B, y0), "x window %d" % it)
     p.destroy()
+
+
+def test_stage_release_hazard_regression():
+    """A stage of the bulk-copy ring must not go back to the producer before the values read from it have
+    arrived.  tests/hazard_stress.py drives every early-releasing kernel with fully
+    scattered gathers at ~226 M entries and compares ALL rows with the independent kernel 3.  The production
+    library must be clean; the same sources built with the pre-fix release (lib/libsblas_spmv_unsafe.so,
+    -DSBLAS_UNSAFE_EARLY_RELEASE) are run too and the outcome is printed: when that build shows wrong rows
+    the input is proven to catch the hazard (it is timing dependent, so a clean run of the unsafe build is
+    not a failure of this test)."""
+    import json
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    libdir = os.path.join(os.path.dirname(here), "s-blas_b200", "lib")
+
+    def run(lib):
+        env = dict(os.environ, SBLAS_LIB=os.path.join(libdir, lib))
+        r = subprocess.run([sys.executable, os.path.join(here, "hazard_stress.py")], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    good = run("libsblas_spmv.so")
+    print("production:", good)
+    assert {3, 6, 7} <= set(good["kinds"]), good          # general (A, W), row-tile and row-split panels all ran
+    assert good["bad"] == 0, good
+    if os.path.exists(os.path.join(libdir, "libsblas_spmv_unsafe.so")):
+        print("pre-fix build:", run("libsblas_spmv_unsafe.so"))
+
+
+def test_graph_replay_of_a_product():
+    """sblas_spmv_plan_step: the first product runs as plain launches, the second is captured into a CUDA graph,
+    later ones replay it; y feeds back (beta != 0) so every product is checked against the oracle applied to the
+    previous result; a change of alpha / beta re-captures.  SBLAS_GRAPH=0 must give bit-identical results."""
+    rng = np.random.default_rng(97)
+    lens = np.concatenate([rng.integers(1, 9, size=9000), [40000, 3, 25000], rng.integers(60, 200, size=8000),
+                           np.full(8192, 2, np.int64)])
+    m, n = len(lens), 20011
+    rp, col, val = make_csr(rng, m, n, lens)
+    val *= 0.01
+    nnz = int(rp[-1])
+    x = rng.uniform(0.5, 1.5, n)
+    results = {}
+    for graph in ("1", "0"):
+        os.environ["SBLAS_GRAPH"] = graph
+        try:
+            p = sb.Plan.create(sb.V1, m, n, nnz, val, rp, col, 1, kernel=1)
+            y = rng.standard_normal(m) if graph == "1" else results["y0"].copy()
+            results.setdefault("y0", y.copy())
+            p.upload(x, y)
+            outs = []
+            for it, (al, be) in enumerate([(A, B), (A, B), (A, B), (A, B), (1.5, 0.25), (1.5, 0.25), (A, B)]):
+                want = oracle.csr_spmv(rp, col, val, x, al, be, y)
+                bound = oracle.csr_spmv_bound(rp, col, val, x, al, be, y)
+                p.step(al, be)
+                got = np.zeros(m)
+                p.download(got)
+                check_tol(got, want, bound, "step %d graph=%s" % (it, graph))
+                y = got
+                outs.append(got)
+            results[graph] = outs
+            p.destroy()
+        finally:
+            os.environ.pop("SBLAS_GRAPH", None)
+    for a, b in zip(results["1"], results["0"]):
+        assert (a == b).all(), "graph replay and stream launches must agree bit for bit"
+
+
+def test_rank_chain_over_peer_x_on_one_device():
+    """The one-process-per-GPU form of the chain, emulated with `world` rank plans on cuda:0 and
+    ordinary device buffers standing in for the peer-mapped x / flag / exchange buffers: every product is
+    sblas_spmv_plan_step (kernels + fused split-row exchange) followed by sblas_spmv_plan_chain (all-gather of the
+    owned y rows into EVERY rank's x with stores + epoch flags); nothing synchronises on the host inside a product.
+    After every product every rank's x must equal the oracle's y bit for bit across ranks and within tolerance."""
+    import torch
+    rng = np.random.default_rng(113)
+    lens = np.concatenate([rng.integers(1, 9, size=3000), [40000, 3, 25000], rng.integers(60, 200, size=800)])
+    m = len(lens)
+    rp, col, val = make_csr(rng, m, m, lens)
+    val *= 0.05
+    nnz = int(rp[-1])
+    for world in (2, 4):
+        plans = [sb.Plan.create_rank(sb.V1, m, m, nnz, val, rp, col, world, r, 0, kernel=1) for r in range(world)]
+        slots = plans[0].edge_slots
+        tw = world * max(slots, 1)
+        tables = [torch.zeros(2 * tw + 2 * world, dtype=torch.float64, device="cuda") for _ in range(world)]
+        xs = [torch.zeros(m, dtype=torch.float64, device="cuda") for _ in range(world)]
+        flags = [torch.zeros(2 * world, dtype=torch.int64, device="cuda") for _ in range(world)]
+        x = rng.uniform(0.5, 1.5, m)
+        for p in plans:
+            p.bind_peer_tables([t.data_ptr() for t in tables], tw)
+            p.bind_peer_x([t.data_ptr() for t in xs], [f.data_ptr() for f in flags])
+            p.upload(x, None)
+        sb.device_synchronize()
+        for it in range(4):
+            want = oracle.csr_spmv(rp, col, val, x, 1.25, 0.0, np.zeros(m))
+            bound = oracle.csr_spmv_bound(rp, col, val, x, 1.25, 0.0, np.zeros(m))
+            for p in plans:
+                p.step(1.25, 0.0)
+            for p in plans:
+                p.chain()
+            sb.device_synchronize()
+            got = [t.cpu().numpy() for t in xs]
+            for r in range(1, world):
+                assert (got[r] == got[0]).all(), (world, it, r)
+            check_tol(got[0], want, bound, "rank chain world=%d product %d" % (world, it))
+            x = got[0]
+        for p in plans:
+            p.destroy()
