@@ -302,14 +302,17 @@ class Problem:
         import torch.distributed as dist
         import sblas_b200 as sb
         self.name, self.rank, self.world, self.local = name, rank, world, local
+        self.partition = "v1"
+        if name.endswith("@bytes"):           # the opt-in byte-balanced partition (not in the reference)
+            name, self.partition = name[:-6], "bytes"
         self.wl = wl = workload(name)
         self.m, self.n = m, n = wl["m"], wl["n"]
         self.lens = lens = wl["row_len"]()
         self.rp = rp = np.zeros(m + 1, np.int64)
         np.cumsum(lens, out=rp[1:])
         self.nnz = nnz = int(rp[-1])
-        version = sb.V1
-        self.parts = parts = sb.partition_v1(rp, world)
+        version = sb.V1 if self.partition == "v1" else sb.V1_BYTES
+        self.parts = parts = sb.partition_v1(rp, world) if self.partition == "v1" else sb.partition_bytes(rp, world)
         self.s_idx, self.e_idx = int(parts["start_idx"][rank]), int(parts["end_idx"][rank])
         self.s_row, self.e_row = int(parts["start_row"][rank]), int(parts["end_row"][rank])
         self.dnnz = dnnz = self.e_idx - self.s_idx + 1
@@ -600,7 +603,9 @@ def measure(name, args, rank, world, local, sampler, steps, warmup, primary):
            "hbm_gbs": alg_total / (ms_step * 1e-3) / 1e9,
            "hbm_frac_of_8000": alg_total / (ms_step * 1e-3) / 1e9 / (8000.0 * world),
            "alg_bytes": alg_total, "parity_check": check, "parity_ok": bool(check["ok"]) if check else None,
-           "clocks": clocks, "config": config_of(name, P.wl, m, n, nnz, world),
+           "clocks": clocks, "config": dict(config_of(P.name.split("@")[0], P.wl, m, n, nnz, world),
+                                            partition=("v1 nnz-balanced x%d" % world) if P.partition == "v1" else
+                                            ("byte-balanced x%d (opt-in, not in the reference: 12 B per entry + 28 B per row)" % world)),
            "panels_rank0": [{"kernel": KNAMES.get(u["kind"], "?"), "rows": u["row_hi"] - u["row_lo"] + 1,
                              "nnz": u["nz1"] - u["nz0"]} for u in P.plan.units()],
            "gpu_launches_per_step": P.launches_per_step}
@@ -802,6 +807,174 @@ def reference_gpu(ngpu):
     return out
 
 
+def spmm_leg(ngpu):
+    """SURVEY section 8f-2 beside the headline: C = alpha*A*B + beta*C, n = 128 (run_test.py:163), the 145.5 M-nnz g-shape
+    matrix resident on ngpu GPUs driven from this process.  Device time of the kernels alone on GPU 0 (CUDA events on the
+    plan's stream, its column slice), whole-call time of the plan's host API on all ngpu GPUs, parity of sampled columns
+    at full size and of every entry on the `g 10000` shape."""
+    import torch
+    import oracle
+    import sblas_b200 as sb
+    oracle.set_threads()
+    out = {"ngpu": ngpu, "n": 128, "alpha": -0.7, "beta": 0.8}
+    # full parity on the small shape
+    name, c = small_host_cases()[1]
+    rp32 = c["rp"].astype(np.int32)
+    rng = np.random.default_rng(9)
+    B = np.asfortranarray(rng.uniform(0, 1, size=(c["n"], 128)))
+    C0 = np.asfortranarray(rng.uniform(0, 1, size=(c["m"], 128)))
+    got = C0.copy(order="F")
+    rc = sb.cusparse_mgpu_csrmm(c["m"], 128, c["n"], -0.7, c["nnz"], rp32, c["col"], c["val"], 0.8, B, got, ngpu)
+    want = oracle.csrmm(rp32, c["col"], c["val"], B, -0.7, 0.8, C0)
+    bound = oracle.csrmm_bound(rp32, c["col"], c["val"], B, -0.7, 0.8, C0)
+    w_small = float((np.abs(got - want) / np.maximum(bound, 1e-300)).max())
+    out["parity_small"] = {"matrix": name, "rc": rc, "max_err_over_bound": w_small, "ok": bool(rc == 0 and w_small <= 1e-12)}
+    # the large shape
+    c = host_problem("inproc")
+    m, k, nnz = c["m"], c["n"], c["nnz"]
+    rp32 = c["rp"].astype(np.int32)
+    p = sb.SpmmPlan(m, k, nnz, rp32, c["col"], c["val"], ngpu)
+    Bh = torch.rand(128, k, dtype=torch.float64).pin_memory()            # column-major k x 128
+    Ch = torch.rand(128, m, dtype=torch.float64).pin_memory()
+    C0 = Ch.clone()
+    Bn, Cn = Bh.numpy().reshape(-1), Ch.numpy().reshape(-1)
+    p.execute(128, -0.7, Bn, 0.8, Cn)
+    cols = [0, 63, 64, 127]
+    Bs = np.asfortranarray(Bh[cols].numpy().T)
+    Cs = np.asfortranarray(C0[cols].numpy().T)
+    want = oracle.csrmm(rp32, c["col"], c["val"], Bs, -0.7, 0.8, Cs)
+    bound = oracle.csrmm_bound(rp32, c["col"], c["val"], Bs, -0.7, 0.8, Cs)
+    w_big = float((np.abs(Ch[cols].numpy().T - want) / np.maximum(bound, 1e-300)).max())
+    ts = []
+    for _ in range(3):
+        Ch.copy_(C0)
+        t0 = time.perf_counter()
+        p.execute(128, -0.7, Bn, 0.8, Cn)
+        ts.append(time.perf_counter() - t0)
+    torch.cuda.set_device(0)               # the in-process calls leave the last GPU current (like the reference's)
+    c0, nd = p.columns(128, 0)
+    dB = Bh[c0:c0 + nd].cuda()
+    dC = C0[c0:c0 + nd].cuda()
+    st = torch.cuda.ExternalStream(p.stream(0))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(st):
+        for _ in range(2):
+            p.execute_device(0, nd, -0.7, dB.data_ptr(), 0.8, dC.data_ptr())
+        e0.record(st)
+        for _ in range(5):
+            p.execute_device(0, nd, -0.7, dB.data_ptr(), 0.8, dC.data_ptr())
+        e1.record(st)
+    e1.synchronize()
+    dev_ms = e0.elapsed_time(e1) / 5
+    p.destroy()
+    out.update({"matrix": c["desc"], "parity_sampled_columns": {"columns": cols, "max_err_over_bound": w_big, "ok": bool(w_big <= 1e-12)},
+                "whole_call_ms": min(ts) * 1e3, "whole_call_gflops": 2.0 * nnz * 128 / min(ts) / 1e9,
+                "gpu0_columns": nd, "gpu0_kernels_ms": dev_ms, "gpu0_kernels_gflops": 2.0 * nnz * nd / (dev_ms * 1e-3) / 1e9,
+                "bound": "on-chip gather of B rows (nd*8 bytes out of L1/L2 per 12 streamed bytes of A): L1 wavefront rate, "
+                         "not HBM and not the FP64 pipe; cuSPARSE SpMM reaches the same rate on this shape",
+                "ok": bool(out["parity_small"]["ok"] and w_big <= 1e-12)})
+    return out
+
+
+def sptrans_leg(ngpu):
+    """SURVEY section 8f-4 beside the headline: CSR -> CSC of the 145.5 M-entry g-shape matrix on ngpu GPUs driven from this
+    process (kernal_sptrans), bit for bit against the oracle's restatement of the reference's host transposition."""
+    import oracle
+    import sblas_b200 as sb
+    c = host_problem("inproc")
+    m, n, nnz = c["m"], c["n"], c["nnz"]
+    rp32 = c["rp"].astype(np.int32)
+    t0 = time.perf_counter()
+    want = oracle.csr2csc(m, n, rp32, c["col"], c["val"])
+    t_cpu = time.perf_counter() - t0
+    sb.kernal_sptrans(m, n, nnz, ngpu, rp32, c["col"], c["val"])            # warm-up (contexts, peer access)
+    t0 = time.perf_counter()
+    rc, colptr, rowidx, val = sb.kernal_sptrans(m, n, nnz, ngpu, rp32, c["col"], c["val"])
+    t_call = time.perf_counter() - t0
+    dev_ms = sb.sptrans_last_device_ms()
+    ok = rc == 0 and bool((colptr == want[0]).all() and (rowidx == want[1]).all() and (val == want[2]).all())
+    passes = max(1, (max(n - 1, 1).bit_length() + 7) // 8)
+    alg = nnz * (16.0 * passes + 4.0 * passes + 12.0 + 24.0)      # per pass: 8 B in + 8 B out + 4 B histogram read; expand; gather
+    return {"ngpu": ngpu, "matrix": c["desc"], "rc": rc, "bit_exact": ok, "ok": ok, "device_ms": dev_ms,
+            "whole_call_ms": t_call * 1e3, "cpu_reference_transposition_ms": t_cpu * 1e3,
+            "entries_per_second_device": nnz / (dev_ms * 1e-3) if dev_ms > 0 else None,
+            "radix_passes": passes, "alg_gbs_device": alg / (dev_ms * 1e-3) / 1e9 if dev_ms > 0 else None}
+
+
+def rank_chain_leg(args, rank, world, local):
+    """SURVEY section 8f-3, one process per GPU: every rank holds its shard of the 145.5 M-nnz g-shape matrix, x lives in
+    symmetric (peer-mapped) memory; three chained products x <- 1.25*A*x, each = sblas_spmv_plan_step (CUDA-graph
+    replay: kernels + fused split-row exchange) + sblas_spmv_plan_chain (all-gather of y into every rank's x with P2P
+    stores + flags).  Rank 0 checks every product's full vector against the oracle."""
+    import torch
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm
+    import oracle
+    import sblas_b200 as sb
+    wl = workload("inproc")
+    m = wl["m"]
+    lens = wl["row_len"]()
+    rp = np.zeros(m + 1, np.int64)
+    np.cumsum(lens, out=rp[1:])
+    nnz = int(rp[-1])
+    parts = sb.partition_v1(rp, world)
+    s_idx, e_idx = int(parts["start_idx"][rank]), int(parts["end_idx"][rank])
+    s_row, e_row = int(parts["start_row"][rank]), int(parts["end_row"][rank])
+    d_val = torch.empty(e_idx - s_idx + 1, dtype=torch.float64, device="cuda")
+    d_col = torch.empty(e_idx - s_idx + 1, dtype=torch.int32, device="cuda")
+    d_rp = torch.from_numpy(rp[s_row:e_row + 2]).cuda()
+    sb.synth_fill_csr(d_rp.data_ptr(), s_row, e_row - s_row + 1, s_idx, e_idx + 1, m, wl["cols_mode"], wl["band"], SEED,
+                      d_val.data_ptr(), d_col.data_ptr())
+    d_val.mul_(1.0 / 4096.0)
+    torch.cuda.synchronize()
+    plan = sb.Plan.create_rank(sb.V1, m, m, nnz, d_val.data_ptr(), rp, d_col.data_ptr(), world, rank, local, kernel=args.kernel,
+                               flags=sb.SRC_DEVICE_SHARD, keep=(d_val, d_col))
+    slots = plan.edge_slots
+    tw = world * max(slots, 1)
+    dev = torch.device("cuda", local)
+    tbuf = symm.empty(2 * tw + 2 * world, dtype=torch.float64, device=dev)
+    xbuf = symm.empty(m, dtype=torch.float64, device=dev)
+    fbuf = symm.empty(2 * world, dtype=torch.int64, device=dev)
+    tbuf.zero_(); fbuf.zero_()
+    h_t, h_x, h_f = (symm.rendezvous(b, dist.group.WORLD) for b in (tbuf, xbuf, fbuf))
+    sb.synth_fill_uniform(xbuf.data_ptr(), m, SEED + 7, 0.0, 1.0)
+    torch.cuda.synchronize()
+    dist.barrier()
+    plan.bind_peer_tables(list(h_t.buffer_ptrs), tw)
+    plan.bind_peer_x(list(h_x.buffer_ptrs), list(h_f.buffer_ptrs))
+    stream = torch.cuda.ExternalStream(plan.stream())
+    ok, worst, times = True, 0.0, []
+    host = None
+    if rank == 0:
+        oracle.set_threads()
+        c = host_problem("inproc")
+        host = (c["rp"], c["col"], c["val"] * (1.0 / 4096.0))
+        x_prev = xbuf.cpu().numpy()
+    for it in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            plan.step(1.25, 0.0)
+            plan.chain()
+            e1.record(stream)
+        e1.synchronize()
+        times.append(allmax(e0.elapsed_time(e1), world))
+        dist.barrier()
+        if rank == 0:
+            x_now = xbuf.cpu().numpy()
+            w, _, _ = oracle.csr_check(host[0], host[1], host[2], x_prev, 1.25, 0.0, np.zeros(m), x_now)
+            worst = max(worst, w)
+            ok = ok and w <= 1e-12
+            x_prev = x_now
+        dist.barrier()
+    plan.destroy()
+    del d_val, d_col
+    torch.cuda.empty_cache()
+    return {"world": world, "products": 3, "ok": bool(ok), "max_err_over_bound": worst, "ms_per_chained_product": times,
+            "what": "plan_step (graph replay: kernels + fused exchange) + plan_chain (P2P all-gather of y into every rank's x), "
+                    "full vector checked on rank 0 after every product"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -844,7 +1017,7 @@ def main():
     main_rec = measure(args.workload, args, rank, world, local, sampler, args.steps, args.warmup, True)
     extras = []
     if extra_on:
-        for name in EXTRA_CONFIGS:
+        for name in EXTRA_CONFIGS + (("big50m@bytes",) if world > 1 else ()):
             try:
                 r = measure(name, args, rank, world, local, sampler, 60, 5, False)
                 extras.append(r)
@@ -855,18 +1028,32 @@ def main():
                 barrier(world)
     api = None
     refgpu = None
+    legs = {}
+    if extra_on and world > 1:
+        try:
+            legs["rank_chain"] = rank_chain_leg(args, rank, world, local)
+        except Exception as ex:
+            legs["rank_chain"] = {"ok": False, "error": repr(ex)}
     if extra_on:
         barrier(world)
         if rank == 0:
+            for key, fn in (("spmm", spmm_leg), ("sptrans", sptrans_leg)):
+                try:
+                    legs[key] = fn(world)
+                except Exception as ex:
+                    legs[key] = {"ok": False, "error": repr(ex)}
+                torch.cuda.set_device(local)
             if world > 1:
                 try:
                     api = inprocess_api(world)
                 except Exception as ex:
                     api = {"ngpu": world, "ok": False, "error": repr(ex)}
+            torch.cuda.set_device(local)
             try:
                 refgpu = reference_gpu(world)
             except Exception as ex:
                 refgpu = {"error": repr(ex)}
+            torch.cuda.set_device(local)
         barrier(world)
 
     if rank == 0:
@@ -936,6 +1123,7 @@ def main():
             out["inprocess_api"] = api
         if refgpu is not None:
             out["reference_gpu"] = refgpu
+        out.update(legs)
         out["job_wall_s"] = time.time() - t_job0
         print(json.dumps(out))
     if sampler is not None:

@@ -116,6 +116,10 @@ cudaError_t sblas_launch_chain_gather(const double *y_src, long long count, long
                                       void *const *peer_flags, int world, int my_rank, unsigned long long *chain_ctr,
                                       cudaStream_t s);
 
+/* load the kernels of the flag protocols (publish / merge-wait / chain) now: their first launch must not happen
+ * while one of them is already spinning on the same device (lazy module loading may synchronise the device) */
+cudaError_t sblas_preload_exchange_kernels(void);
+
 /* device fill helpers used by the plan */
 cudaError_t sblas_launch_fill_f64(double *p, long long n, double v, cudaStream_t s);
 

@@ -68,6 +68,9 @@ typedef struct sblas_part {
 int sblas_partition_baseline(int m, const long long *csrRowPtr, int ngpu, sblas_part *out);
 /* spmv/src/dspmv_mgpu_v1.cu:59-100,119 */
 int sblas_partition_v1(int m, long long nnz, const long long *csrRowPtr, int ngpu, sblas_part *out);
+/* NOT in the reference, opt-in (version SBLAS_V1_BYTES): v1's contiguous nnz ranges with split rows, cut at equal
+ * shares of the streamed BYTES (12 per entry + row_bytes per row) instead of equal entry counts */
+int sblas_partition_bytes(int m, long long nnz, const long long *csrRowPtr, int ngpu, int row_bytes, sblas_part *out);
 /* spmv/src/dspmv_mgpu_v2.cu:218 (task count) and :211-275 (generate_tasks) */
 int sblas_v2_num_tasks(long long nnz, long long nb);
 int sblas_generate_tasks_v2(int m, long long nnz, const long long *csrRowPtr, long long nb, sblas_part *out);
@@ -87,7 +90,8 @@ void sblas_local_rowptr(const long long *csrRowPtr, const sblas_part *p, int bas
  */
 typedef struct sblas_spmv_plan sblas_spmv_plan;
 
-enum { SBLAS_BASELINE = 0, SBLAS_V1 = 1, SBLAS_V2 = 2 };
+enum { SBLAS_BASELINE = 0, SBLAS_V1 = 1, SBLAS_V2 = 2, SBLAS_V1_BYTES = 3 /* byte-balanced v1, opt-in, not in the reference */ };
+#define SBLAS_ROW_BYTES 28      /* per-row weight of SBLAS_V1_BYTES: row pointer 4 + y read and write 16 + x 8 */
 
 /* In-process multi-GPU plan on devices 0..ngpu-1 from HOST arrays (pinned or
  * pageable).  version: SBLAS_*.  nb / q are only used by SBLAS_V2. */

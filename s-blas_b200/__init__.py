@@ -19,7 +19,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SBLAS_LIB") or os.path.join(_HERE, "lib", "libsblas_spmv.so")   # SBLAS_LIB: A/B builds
 
-BASELINE, V1, V2 = 0, 1, 2
+BASELINE, V1, V2, V1_BYTES = 0, 1, 2, 3
+ROW_BYTES = 28
 SRC_HOST, SRC_DEVICE_SHARD, LAYOUT_ONLY = 0, 1, 2
 K_VECTOR, K_TILE, K_TMA, K_VECP = 1, 2, 3, 4
 COLS_PREFIX, COLS_BANDED, COLS_UNIFORM, COLS_CIRCUIT, COLS_BANDRUN = 0, 1, 2, 3, 4
@@ -71,6 +72,7 @@ def lib():
     L.sblas_get_gpu_availble_mem.restype = C.c_double
     L.sblas_partition_baseline.argtypes = [C.c_int, _vp, C.c_int, P(Part)]
     L.sblas_partition_v1.argtypes = [C.c_int, _LL, _vp, C.c_int, P(Part)]
+    L.sblas_partition_bytes.argtypes = [C.c_int, _LL, _vp, C.c_int, C.c_int, P(Part)]
     L.sblas_v2_num_tasks.argtypes = [_LL, _LL]
     L.sblas_generate_tasks_v2.argtypes = [C.c_int, _LL, _vp, _LL, P(Part)]
     L.sblas_v2_task_owner.argtypes = [C.c_int, C.c_int, C.c_int]
@@ -243,6 +245,15 @@ def partition_v1(csrRowPtr, ngpu):
     rp = _host(csrRowPtr, np.int64, "csrRowPtr")
     arr = (Part * ngpu)()
     rc = lib().sblas_partition_v1(len(rp) - 1, int(rp[-1]), _ptr(rp), ngpu, arr)
+    assert rc == 0
+    return _parts_to_dict(arr, ngpu)
+
+
+def partition_bytes(csrRowPtr, ngpu, row_bytes=ROW_BYTES):
+    """Opt-in byte-balanced variant of the v1 partition (not in the reference)."""
+    rp = _host(csrRowPtr, np.int64, "csrRowPtr")
+    arr = (Part * ngpu)()
+    rc = lib().sblas_partition_bytes(len(rp) - 1, int(rp[-1]), _ptr(rp), ngpu, row_bytes, arr)
     assert rc == 0
     return _parts_to_dict(arr, ngpu)
 

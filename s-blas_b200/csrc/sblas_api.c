@@ -76,12 +76,20 @@ static int one_shot(int version, int m, int n, long long nnz, double *alpha, dou
         return sblas_spmv_plan_execute(g_cache[slot].plan, alpha, x, beta, y) == 0 ? 0 : -1;
     }
     sblas_spmv_plan *plan = NULL;
+    const int timing = getenv("SBLAS_TIMING") != NULL;
+    const double t0 = timing ? sblas_get_time() : 0.0;
     int rc = sblas_spmv_plan_create(&plan, version, m, n, nnz, val, rp, col, ngpu, kernel, nb, q);
     if (rc != 0) {
         if (getenv("SBLAS_VERBOSE")) fprintf(stderr, "sblas: %s\n", sblas_last_error());
         return rc;
     }
+    const double t1 = timing ? sblas_get_time() : 0.0;
     rc = sblas_spmv_plan_execute(plan, alpha, x, beta, y);
+    if (timing) {
+        const double t2 = sblas_get_time();
+        fprintf(stderr, "sblas one-shot version %d ngpu %d: plan %.3f ms (%d segments, %d launches), execute %.3f ms\n", version,
+                ngpu, (t1 - t0) * 1e3, sblas_spmv_plan_num_segments(plan), sblas_spmv_plan_launches(plan), (t2 - t1) * 1e3);
+    }
     if (rc != 0) {
         if (getenv("SBLAS_VERBOSE")) fprintf(stderr, "sblas: %s\n", sblas_last_error());
         rc = -1;                                   /* kernel / copy failure: dspmv_mgpu_v1.cu:226-228 */

@@ -775,6 +775,23 @@ extern "C" cudaError_t sblas_launch_edge_merge_wait(const int *mrow, const int *
     return cudaGetLastError();
 }
 
+/* The flag protocols above have kernels that SPIN until another kernel has run.  With CUDA's lazy module loading
+ * the FIRST launch of a kernel may synchronise the device: launching, say, chain_copy_kernel for the first time while
+ * chain_ready_kernel spins on the same device (several rank plans sharing one GPU, as in the tests) would block the
+ * host behind a kernel that waits for a kernel the host has not launched yet.  Loading them up front (at bind time)
+ * removes that window. */
+extern "C" cudaError_t sblas_preload_exchange_kernels(void)
+{
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, edge_publish_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, edge_merge_wait_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, chain_ready_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, chain_copy_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, chain_done_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, edge_merge_kernel);
+    return e;
+}
+
 extern "C" cudaError_t sblas_launch_chain_gather(const double *y_src, long long count, long long dst_off,
                                                  void *const *peer_x, void *const *peer_flags, int world, int my_rank,
                                                  unsigned long long *chain_ctr, cudaStream_t s)

@@ -173,6 +173,7 @@ static int build_global(sblas_spmv_plan *P, const long long *rp)
 
     if (P->version == SBLAS_BASELINE) sblas_partition_baseline(m, rp, G, P->parts);
     else if (P->version == SBLAS_V1) sblas_partition_v1(m, P->nnz, rp, G, P->parts);
+    else if (P->version == SBLAS_V1_BYTES) sblas_partition_bytes(m, P->nnz, rp, G, env_int("SBLAS_ROW_BYTES", SBLAS_ROW_BYTES), P->parts);
     else sblas_generate_tasks_v2(m, P->nnz, rp, P->nb, P->parts);
 
     int prev = -1;                 /* previous non-empty segment */
@@ -1228,6 +1229,7 @@ int sblas_spmv_plan_bind_peer_tables(sblas_spmv_plan *P, void *const *peer_bases
     }
     if (D->seg_begin >= 0 || 1) {
         CU(cudaSetDevice(D->device >= 0 ? D->device : 0));
+        CU(sblas_preload_exchange_kernels());
         CU(cudaMalloc((void **)&P->d_peer_bases, (size_t)W * sizeof(void *)));
         CU(cudaMemcpy(P->d_peer_bases, peer_bases, (size_t)W * sizeof(void *), cudaMemcpyHostToDevice));
         CU(cudaMalloc((void **)&P->d_out_slot, (size_t)(nout + 1) * sizeof(int)));
@@ -1351,6 +1353,7 @@ int sblas_spmv_plan_bind_peer_x(sblas_spmv_plan *P, void *const *peer_x, void *c
     if (!P->rank_mode || P->dry || !peer_x || !peer_flags) return -1;
     sblas_dev *D = &P->devs[0];
     CU(cudaSetDevice(D->device >= 0 ? D->device : 0));
+    CU(sblas_preload_exchange_kernels());
     if (!P->d_peer_x) {
         CU(cudaMalloc((void **)&P->d_peer_x, (size_t)P->world * sizeof(void *)));
         CU(cudaMalloc((void **)&P->d_peer_xflags, (size_t)P->world * sizeof(void *)));

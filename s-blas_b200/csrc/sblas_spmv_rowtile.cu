@@ -100,10 +100,13 @@ __device__ __forceinline__ void rt_produce(const sblas_seg_args &a, RtStage *st,
     }
 }
 
-/* NS = slots per lane: the panel's R rows hold at most 32*NS entries */
-template <int NS>
-__global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas_seg_args a, const int R)
+/* NS = slots per lane: the panel's R rows hold at most 32*NS entries.  RT = R known at compile time (1 or 2: the
+ * two shapes that carry the benchmark configs, rows of 129..256 and of 86..128 entries) or 0 = R from the argument;
+ * with RT the other reductions are pruned and R == 1 reads its two row boundaries with broadcast loads. */
+template <int NS, int RT>
+__global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas_seg_args a, const int Rarg)
 {
+    const int R = RT ? RT : Rarg;
     extern __shared__ __align__(128) unsigned char smem[];
     RtStage *st = reinterpret_cast<RtStage *>(smem);
     const uint32_t smem0 = smem_u32(smem);
@@ -140,8 +143,10 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas
     const bool has_y = a.beta != 0.0;
     double *P = scratch + warp * kRtScratch;
 
-    /* state of the tile whose x values sit in xv */
-    double xv[NS];
+    /* xv: the x values of the tile being multiplied; xvn: those of the NEXT tile, whose gathers are issued at the top
+     * of the iteration -- a whole tile's products and row sums ahead of their use (with the gathers issued only after
+     * the products, 19 % of the stall samples sat on the multiply waiting for x: profiles/r01_ncu_hotspots_*rowtile*) */
+    double xv[NS], xvn[NS];
     int cb = 0, ce = 0;       /* my rows' entries, stage-local [cb, ce) */
     int first = 0, nr = 0;    /* my rows: first (GPU-local row id) and how many */
     int v = kWin;             /* lane q < nr-1: where row first+q+1 starts, relative to cb; else kWin */
@@ -153,14 +158,20 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas
         nr = min(R, S.nrows - mine0);
         first = r0 + mine0;
         const int *rp = S.rp + S.rp_off + mine0;
-        /* lane q <= nr reads the q-th boundary of my rows */
-        int b = 0;
-        if (lane <= nr) b = min(max(rp[lane], a.nz0), a.nz1) - S.s0;
-        cb = __shfl_sync(kFull, b, 0);
-        ce = __shfl_sync(kFull, b, nr);
-        const int nxt = __shfl_down_sync(kFull, b, 1);
-        v = (lane + 1 < nr) ? nxt - cb : kWin;
-        {
+        if (RT == 1) {
+            /* one row: both boundaries with broadcast loads, no shuffles */
+            cb = min(max(rp[0], a.nz0), a.nz1) - S.s0;
+            ce = nr > 0 ? min(max(rp[1], a.nz0), a.nz1) - S.s0 : cb;
+            yv = 0.0;
+            if (has_y && lane == 0 && nr > 0 && first != a.skip_first && first != a.skip_last) yv = a.y[first];
+        } else {
+            /* lane q <= nr reads the q-th boundary of my rows */
+            int b = 0;
+            if (lane <= nr) b = min(max(rp[lane], a.nz0), a.nz1) - S.s0;
+            cb = __shfl_sync(kFull, b, 0);
+            ce = __shfl_sync(kFull, b, nr);
+            const int nxt = __shfl_down_sync(kFull, b, 1);
+            v = (lane + 1 < nr) ? nxt - cb : kWin;
             const int row = first + (lane >> 2);
             yv = 0.0;
             if (has_y && (lane & 3) == 0 && (lane >> 2) < nr && row != a.skip_first && row != a.skip_last) yv = a.y[row];
@@ -168,8 +179,8 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
             const int pos = cb + 32 * i + lane;
-            xv[i] = 0.0;
-            if (pos < ce) xv[i] = __ldg(xp + (unsigned)S.col[pos]);
+            xvn[i] = 0.0;
+            if (pos < ce) xvn[i] = __ldg(xp + (unsigned)S.col[pos]);
         }
     };
 
@@ -186,6 +197,14 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas
         const bool has_next = j + ncta < ntile;
         const int ccb = cb, cce = ce, cfirst = first, cnr = nr, cv = v;
         const double cyv = yv;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) xv[i] = xvn[i];
+
+        /* (0) the next tile's col reads + x gathers go out first */
+        if (has_next) {
+            mbar_wait(full0 + 8u * sn, phn);
+            gather(st[sn], j + ncta);
+        }
 
         /* (1) products; slots past the end of my rows are zero */
         double p[NS];
@@ -207,12 +226,6 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas
         const int myrow = cfirst + pc;
         const bool owner = (lane & 3) == 0 && pc < cnr;
 
-        /* (2) the next tile's gathers go out before the sums */
-        if (has_next) {
-            mbar_wait(full0 + 8u * sn, phn);
-            gather(st[sn], j + ncta);
-        }
-
         /* (3) row sums */
         double mine;
         if (R == 1) {
@@ -225,12 +238,13 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas
             for (int i = 0; i < NS; ++i) {
                 if (32 * i < bnd) a0 += p[i]; else a1 += p[i];
             }
+            /* one folded butterfly instead of two: the lower half-warp collects row 0, the upper one row 1 */
+            const bool up = (lane & 16) != 0;
+            double t2 = (up ? a1 : a0) + __shfl_xor_sync(kFull, up ? a0 : a1, 16);
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                a0 += __shfl_xor_sync(kFull, a0, off);
-                a1 += __shfl_xor_sync(kFull, a1, off);
-            }
-            mine = pc == 0 ? a0 : a1;
+            for (int off = 8; off > 0; off >>= 1) t2 += __shfl_xor_sync(kFull, t2, off);
+            const double r1 = __shfl_sync(kFull, t2, 16);
+            mine = pc == 0 ? t2 : r1;
         } else {
             double acc = 0.0;
             int cur = 0;
@@ -322,7 +336,7 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowsplit_kernel(const sbla
     const int rr = warp / G, part = warp - rr * G;      /* my row of the tile, my piece of that row */
 
     constexpr int NS = kWin / 32;
-    double xv[NS];
+    double xv[NS], xvn[NS];   /* current tile's x values / the next tile's, gathered a whole tile ahead (see spmv_rowtile_kernel) */
     int cb = 0, ce = 0;       /* my piece, stage-local [cb, ce) */
     int trows = 0;            /* rows of the tile */
     double yv = 0.0;          /* warp 0, lane l < trows: y of the tile's row l */
@@ -346,8 +360,8 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowsplit_kernel(const sbla
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
             const int pos = cb + 32 * i + lane;
-            xv[i] = 0.0;
-            if (pos < ce) xv[i] = __ldg(xp + (unsigned)S.col[pos]);
+            xvn[i] = 0.0;
+            if (pos < ce) xvn[i] = __ldg(xp + (unsigned)S.col[pos]);
         }
     };
 
@@ -366,6 +380,12 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowsplit_kernel(const sbla
         const int ccb = cb, cce = ce, ctrows = trows;
         const double cyv = yv;
         const int ring = (int)(it & (kSplitRing - 1));
+#pragma unroll
+        for (int i = 0; i < NS; ++i) xv[i] = xvn[i];
+        if (has_next) {                                           /* the next tile's gathers go out first */
+            mbar_wait(full0 + 8u * sn, phn);
+            gather(st[sn], j + ncta);
+        }
 
         double t0 = 0.0, t1 = 0.0;
 #pragma unroll
@@ -375,11 +395,6 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowsplit_kernel(const sbla
             if (pos + 32 < cce) t1 = fma(S.val[pos + 32], xv[i + 1], t1);
         }
         release_after(empty0 + 8u * s, lane, t0 + t1);              /* the stage goes back once its values are in registers */
-
-        if (has_next) {
-            mbar_wait(full0 + 8u * sn, phn);
-            gather(st[sn], j + ncta);
-        }
 
         const double mine = warp_sum(t0 + t1);
         double *R = red + ring * kRtWarps;
@@ -413,7 +428,9 @@ cudaError_t sblas_launch_rowtile(const sblas_seg_args *a, int R, int window, cud
     if (dev >= 64 || R < 1 || R > 8) return cudaErrorInvalidValue;
     if (!attr_done[dev]) {
         cudaError_t e = cudaSuccess;
-#define RT_ATTR(NS) if (e == cudaSuccess) e = cudaFuncSetAttribute(spmv_rowtile_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmem)
+#define RT_ATTR(NS) if (e == cudaSuccess) e = cudaFuncSetAttribute(spmv_rowtile_kernel<NS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmem); \
+                    if (e == cudaSuccess) e = cudaFuncSetAttribute(spmv_rowtile_kernel<NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmem); \
+                    if (e == cudaSuccess) e = cudaFuncSetAttribute(spmv_rowtile_kernel<NS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmem)
         RT_ATTR(4); RT_ATTR(5); RT_ATTR(6); RT_ATTR(7); RT_ATTR(8);
 #undef RT_ATTR
         if (e != cudaSuccess) return e;
@@ -428,13 +445,17 @@ cudaError_t sblas_launch_rowtile(const sblas_seg_args *a, int R, int window, cud
     if (grid > ntile) grid = ntile;
     int ns = (window + 31) / 32;
     if (window <= 0 || ns > 8) ns = 8;
+#define RT_LAUNCH(NS) do { if (R == 1) spmv_rowtile_kernel<NS, 1><<<grid, kRtThreads, kRtSmem, s>>>(*a, R); \
+                           else if (R == 2) spmv_rowtile_kernel<NS, 2><<<grid, kRtThreads, kRtSmem, s>>>(*a, R); \
+                           else spmv_rowtile_kernel<NS, 0><<<grid, kRtThreads, kRtSmem, s>>>(*a, R); } while (0)
     switch (ns) {
-    case 1: case 2: case 3: case 4: spmv_rowtile_kernel<4><<<grid, kRtThreads, kRtSmem, s>>>(*a, R); break;
-    case 5: spmv_rowtile_kernel<5><<<grid, kRtThreads, kRtSmem, s>>>(*a, R); break;
-    case 6: spmv_rowtile_kernel<6><<<grid, kRtThreads, kRtSmem, s>>>(*a, R); break;
-    case 7: spmv_rowtile_kernel<7><<<grid, kRtThreads, kRtSmem, s>>>(*a, R); break;
-    default: spmv_rowtile_kernel<8><<<grid, kRtThreads, kRtSmem, s>>>(*a, R); break;
+    case 1: case 2: case 3: case 4: RT_LAUNCH(4); break;
+    case 5: RT_LAUNCH(5); break;
+    case 6: RT_LAUNCH(6); break;
+    case 7: RT_LAUNCH(7); break;
+    default: RT_LAUNCH(8); break;
     }
+#undef RT_LAUNCH
     return cudaGetLastError();
 }
 

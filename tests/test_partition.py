@@ -118,3 +118,27 @@ def test_layout_only_plan_lists_one_panel_per_segment():
                 assert (u["row_lo"], u["row_hi"], u["nz0"], u["nz1"]) == (s["row_lo"], s["row_hi"], s["nz0"], s["nz1"])
                 assert u["kind"] in (1, 3)          # lanes-per-row below 65,536 entries per GPU, else the TMA kernel
             p.destroy()
+
+
+def test_byte_balanced_partition_properties():
+    """The opt-in fourth version (not in the reference): contiguous nnz ranges covering [0, nnz) like v1, rows and flags
+    from the same lookups, every shard within one row's weight of an equal share of 12*nnz + 28*rows bytes."""
+    import sblas_b200 as sb
+    rng = np.random.default_rng(5)
+    for lens in (np.concatenate([np.full(6250, 180, np.int64), np.full(43750, 2, np.int64)]),
+                 rng.integers(1, 50, size=20000), np.concatenate([[100000], rng.integers(1, 9, size=5000)])):
+        rp = np.zeros(len(lens) + 1, np.int64)
+        rp[1:] = np.cumsum(lens)
+        m, nnz = len(lens), int(rp[-1])
+        for g in (1, 2, 3, 8):
+            p = sb.partition_bytes(rp, g)
+            assert p["start_idx"][0] == 0 and p["end_idx"][-1] == nnz - 1
+            assert (p["start_idx"][1:] == p["end_idx"][:-1] + 1).all()
+            share = (12.0 * nnz + 28.0 * m) / g
+            for i in range(g):
+                s, e = int(p["start_idx"][i]), int(p["end_idx"][i])
+                r0 = int(np.searchsorted(rp, s, side="right")) - 1
+                r1 = int(np.searchsorted(rp, e + 1, side="right")) - 1
+                w = 12.0 * (e + 1 - s) + 28.0 * (r1 - r0)
+                assert abs(w - share) <= 12.0 * lens.max() + 56.0, (g, i, w, share)
+                assert p["start_row"][i] == sb.get_row_from_index(m, rp, s) and p["end_row"][i] == sb.get_row_from_index(m, rp, e)

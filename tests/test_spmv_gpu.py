@@ -575,13 +575,17 @@ def test_graph_replay_of_a_product():
         assert (a == b).all(), "graph replay and stream launches must agree bit for bit"
 
 
-def test_rank_chain_over_peer_x_on_one_device():
+def test_rank_chain_over_peer_x_on_one_device(monkeypatch):
     """The one-process-per-GPU form of the chain, emulated with `world` rank plans on cuda:0 and
-    ordinary device buffers standing in for the peer-mapped x / flag / exchange buffers: every product is
-    sblas_spmv_plan_step (kernels + fused split-row exchange) followed by sblas_spmv_plan_chain (all-gather of the
-    owned y rows into EVERY rank's x with stores + epoch flags); nothing synchronises on the host inside a product.
-    After every product every rank's x must equal the oracle's y bit for bit across ranks and within tolerance."""
+    ordinary device buffers standing in for the peer-mapped x / flag / exchange buffers.  Per product: the segments,
+    the fused split-row exchange (publish, then merge -- stepped in phases, because on ONE device a kernel that
+    spins on a flag must never wait for a kernel the host has not launched yet; graph replay is off for the same
+    reason: instantiating a graph may block on the device) and sblas_spmv_plan_chain (all-gather of the owned y
+    rows into EVERY rank's x with stores + epoch flags; its three small kernels per rank are launched back to back for
+    all ranks).  After every product every rank's x equals the others' bit for bit and the oracle's y within
+    tolerance.  The real multi-process path (graph replay included) is exercised by bench.py's rank_chain leg."""
     import torch
+    monkeypatch.setenv("SBLAS_GRAPH", "0")
     rng = np.random.default_rng(113)
     lens = np.concatenate([rng.integers(1, 9, size=3000), [40000, 3, 25000], rng.integers(60, 200, size=800)])
     m = len(lens)
@@ -605,8 +609,14 @@ def test_rank_chain_over_peer_x_on_one_device():
             want = oracle.csr_spmv(rp, col, val, x, 1.25, 0.0, np.zeros(m))
             bound = oracle.csr_spmv_bound(rp, col, val, x, 1.25, 0.0, np.zeros(m))
             for p in plans:
-                p.step(1.25, 0.0)
+                p.execute_device(1.25, 0.0, sync=True)
             for p in plans:
+                p.exchange_merge(1.25, 0.0, phase=1)
+            sb.device_synchronize()
+            for p in plans:
+                p.exchange_merge(1.25, 0.0, phase=2)
+            sb.device_synchronize()
+            for p in plans:                          # kernel launches only: all ranks' flag kernels get to run together
                 p.chain()
             sb.device_synchronize()
             got = [t.cpu().numpy() for t in xs]
@@ -616,3 +626,46 @@ def test_rank_chain_over_peer_x_on_one_device():
             x = got[0]
         for p in plans:
             p.destroy()
+
+
+def test_byte_balanced_version(qh768):
+    """SBLAS_V1_BYTES (opt-in, not in the reference): same machinery as v1 on differently placed cuts -- in-process
+    plans on every visible GPU count and rank plans emulating 8 GPUs with the gathered-table merge."""
+    rng = np.random.default_rng(131)
+    lens = np.concatenate([np.full(3000, 180, np.int64), np.full(60000, 2, np.int64), [30000], rng.integers(1, 60, size=4000)])
+    rp, col, val = make_csr(rng, len(lens), 9001, lens)
+    m, n, nnz = len(lens), 9001, int(rp[-1])
+    x, y0 = rng.standard_normal(n), rng.standard_normal(m)
+    want = oracle.csr_spmv(rp, col, val, x, A, B, y0)
+    bound = oracle.csr_spmv_bound(rp, col, val, x, A, B, y0)
+    for g in gpu_counts():
+        p = sb.Plan.create(sb.V1_BYTES, m, n, nnz, val, rp, col, g, kernel=1)
+        y = y0.copy()
+        p.execute(A, x, B, y)
+        check_tol(y, want, bound, "byte-balanced in-process ngpu=%d" % g)
+        p.destroy()
+    world = 8
+    plans = [sb.Plan.create_rank(sb.V1_BYTES, m, n, nnz, val, rp, col, world, r, 0, kernel=1) for r in range(world)]
+    slots = plans[0].edge_slots
+    table = np.zeros(world * max(slots, 1))
+    y = y0.copy()
+    for r, p in enumerate(plans):
+        p.execute(A, x, B, y)
+        if slots:
+            sb.memcpy(table[r * slots:], p.edge_ptr(), 8 * slots, 2)
+    d_table = plans[0].x_ptr()
+    sb.memcpy(d_table, table, 8 * world * slots, 1)
+    parts = sb.partition_bytes(rp, world)
+    for r, p in enumerate(plans):
+        p.merge_gathered(d_table, A, B)
+        sb.device_synchronize()
+        ptr, first, rows = p.y_ptr()
+        if rows == 0:
+            continue
+        ybuf = np.zeros(rows)
+        sb.memcpy(ybuf, ptr, 8 * rows, 2)
+        skip = 1 if parts["start_flag"][r] else 0
+        y[first + skip:first + rows] = ybuf[skip:]
+    check_tol(y, want, bound, "byte-balanced rank plans world=8")
+    for p in plans:
+        p.destroy()

@@ -15,5 +15,7 @@ for c in d.get("configs", []):
 a=d.get("inprocess_api") or {}
 print("inprocess ok", a.get("ok"), a.get("error"), [(c["matrix"][:8], c["entry"], round(c["ms_whole_call"],1), c["ok"]) for c in a.get("calls", [])], a.get("chain"))
 print("refgpu", d.get("reference_gpu"))
+for k in ("rank_chain", "spmm", "sptrans"):
+    print(k, d.get(k))
 print("wall", d.get("job_wall_s"))
 PY
