@@ -12,6 +12,9 @@
  * the -m gpu tests compare this repo's library with it on the same host arrays, and
  * tests/golden/make_golden_y.py commits its y vectors as fixtures.
  *
+ * One limit of the mapping: cusparseCreateCsr refuses nnz > rows*cols (a shard of a matrix whose rows repeat a
+ * column can exceed it); the legacy routines did not check.  The tests leave such v2 tasks out.
+ *
  * Same argument conventions as the legacy calls: alpha/beta are host pointers (pointer mode host),
  * int32 base-0 CSR, y = alpha*op(A)*x + beta*y, work enqueued on the handle's stream.
  */

@@ -12,15 +12,17 @@
  *     spmv_helper.cu compiled into oracle/_ref/libref_helper.so (see
  *     oracle/Makefile) and (b) golden vectors in tests/golden/ produced from that
  *     object and from the reference's sample matrix by tests/golden/make_golden.py.
- *   - the arithmetic itself (the csrmv call): "parity unpinned" in absolute terms.
- *     The reference delegates it to closed-source legacy cuSPARSE
- *     (cusparseDcsrmv / cusparseDcsrmv_mp, CUDA Toolkit <= 10.2, removed in 11.0;
- *     call sites spmv/src/dspmv_mgpu_baseline.cu:163, dspmv_mgpu_v1.cu:200,206,
- *     dspmv_mgpu_v2.cu:351,357) and ships no golden y vectors.  What is pinned is
- *     the documented definition y = alpha*A*x + beta*y (README.md:122-123,
- *     spmv/INSTALL.md:117-118) plus the reference's merge arithmetic for rows
- *     that are split between GPUs/tasks (dspmv_mgpu_v1.cu:235-248,
- *     dspmv_mgpu_v2.cu:385-441), both restated here.
+ *   - the arithmetic itself (the csrmv call): PINNED since round 2.  The reference delegates it to
+ *     legacy cuSPARSE (cusparseDcsrmv / cusparseDcsrmv_mp, removed in CUDA 11; call sites
+ *     spmv/src/dspmv_mgpu_baseline.cu:163, dspmv_mgpu_v1.cu:200,206, dspmv_mgpu_v2.cu:351,357) and
+ *     ships no golden y vectors; oracle/compat_csrmv.h maps the two removed names onto cusparseSpMV, so
+ *     the reference's own unmodified entry points compile into oracle/_ref/libref_spmv.so and run on the
+ *     GPU box.  tests/golden/ref_y.npz holds the y vectors they produced on a B200
+ *     (tests/golden/make_golden_y.py); tests/test_reference_y.py checks this file's csrmv and its
+ *     restatements of the whole entry points (partition, per-shard csrmv, the host merges of
+ *     dspmv_mgpu_v1.cu:235-248 and dspmv_mgpu_v2.cu:385-441) against them on the CPU, and the library
+ *     against them and against the reference code run live on the GPU.
+ *   - SpMM (oracle_csrmm) and the transposition (oracle_csr2csc): see the notes at those functions.
  *
  * Every function cites the reference file:line it follows.  Paths are relative
  * to the reference checkout.

@@ -100,9 +100,11 @@ __device__ __forceinline__ void rt_produce(const sblas_seg_args &a, RtStage *st,
     }
 }
 
-/* NS = slots per lane: the panel's R rows hold at most 32*NS entries.  RT = R known at compile time (1 or 2: the
- * two shapes that carry the benchmark configs, rows of 129..256 and of 86..128 entries) or 0 = R from the argument;
- * with RT the other reductions are pruned and R == 1 reads its two row boundaries with broadcast loads. */
+/* NS = slots per lane: the panel's R rows hold at most 32*NS entries.  RT = R when it is a power of two (1, 2, 4, 8:
+ * rows of 129..256, 65..128, 33..64, <= 32 entries), else 0 = R from the argument.  With RT the warp is cut into RT
+ * LANE GROUPS of L = 32/RT lanes, one row each: slot i of lane l is entry (l % L) + L*i of row l / L, every group
+ * reads its two row boundaries with broadcast loads, and ONE butterfly over log2(L) levels finishes all RT rows at
+ * once -- no row-split predicates, no scratch, no transposed pass (round 2; the general RT = 0 path keeps them). */
 template <int NS, int RT>
 __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas_seg_args a, const int Rarg)
 {
@@ -158,13 +160,25 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas
         nr = min(R, S.nrows - mine0);
         first = r0 + mine0;
         const int *rp = S.rp + S.rp_off + mine0;
-        if (RT == 1) {
-            /* one row: both boundaries with broadcast loads, no shuffles */
-            cb = min(max(rp[0], a.nz0), a.nz1) - S.s0;
-            ce = nr > 0 ? min(max(rp[1], a.nz0), a.nz1) - S.s0 : cb;
+        if (RT > 0) {
+            /* lane groups: my group's row, both boundaries with (group-)broadcast loads, no shuffles */
+            constexpr int L = 32 / (RT > 0 ? RT : 1);
+            const int g = lane / L;
+            const bool has = g < nr;
+            cb = has ? min(max(rp[g], a.nz0), a.nz1) - S.s0 : 0;
+            ce = has ? min(max(rp[g + 1], a.nz0), a.nz1) - S.s0 : cb;
+            const int row = first + g;
             yv = 0.0;
-            if (has_y && lane == 0 && nr > 0 && first != a.skip_first && first != a.skip_last) yv = a.y[first];
-        } else {
+            if (has_y && has && (lane % L) == 0 && row != a.skip_first && row != a.skip_last) yv = a.y[row];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                const int pos = cb + L * i + (lane % L);
+                xvn[i] = 0.0;
+                if (pos < ce) xvn[i] = __ldg(xp + (unsigned)S.col[pos]);
+            }
+            return;
+        }
+        {
             /* lane q <= nr reads the q-th boundary of my rows */
             int b = 0;
             if (lane <= nr) b = min(max(rp[lane], a.nz0), a.nz1) - S.s0;
@@ -207,45 +221,38 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas
         }
 
         /* (1) products; slots past the end of my rows are zero */
+        constexpr int L = RT > 0 ? 32 / (RT > 0 ? RT : 1) : 32;      /* lanes per row (RT > 0) / stride of the slots */
+        const int q0 = RT > 0 ? (lane % L) : lane;
         double p[NS];
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
-            const int pos = ccb + 32 * i + lane;
+            const int pos = ccb + L * i + q0;
             p[i] = (pos < cce) ? S.val[pos] * xv[i] : 0.0;
         }
         double psum = p[0], psum1 = p[1];                  /* every product: the witness of the release, and */
 #pragma unroll
-        for (int i = 2; i < NS; i += 2) psum += p[i];      /* the row sum itself when R == 1               */
+        for (int i = 2; i < NS; i += 2) psum += p[i];      /* my lane's share of its row's sum when RT > 0   */
 #pragma unroll
         for (int i = 3; i < NS; i += 2) psum1 += p[i];
         psum += psum1;
         release_after(empty0 + 8u * s, lane, psum);        /* the stage goes back once its values are in registers */
 
-        /* lane 4c owns row cfirst + c (R == 1: lane 0) */
-        const int pc = lane >> 2;
-        const int myrow = cfirst + pc;
-        const bool owner = (lane & 3) == 0 && pc < cnr;
-
         /* (3) row sums */
         double mine;
-        if (R == 1) {
-            mine = warp_sum(psum);
-        } else if (R == 2) {
-            /* two rows: two accumulators split at the second row's start, two interleaved reductions */
-            const int bnd = __shfl_sync(kFull, cv, 0) - lane;     /* slot i belongs to row 0 iff 32*i < bnd */
-            double a0 = 0.0, a1 = 0.0;
+        int myrow;
+        bool owner;
+        if (RT > 0) {
+            /* one butterfly inside every lane group finishes all RT rows at once */
+            mine = psum;
 #pragma unroll
-            for (int i = 0; i < NS; ++i) {
-                if (32 * i < bnd) a0 += p[i]; else a1 += p[i];
-            }
-            /* one folded butterfly instead of two: the lower half-warp collects row 0, the upper one row 1 */
-            const bool up = (lane & 16) != 0;
-            double t2 = (up ? a1 : a0) + __shfl_xor_sync(kFull, up ? a0 : a1, 16);
-#pragma unroll
-            for (int off = 8; off > 0; off >>= 1) t2 += __shfl_xor_sync(kFull, t2, off);
-            const double r1 = __shfl_sync(kFull, t2, 16);
-            mine = pc == 0 ? t2 : r1;
+            for (int off = L >> 1; off > 0; off >>= 1) mine += __shfl_xor_sync(kFull, mine, off);
+            myrow = cfirst + lane / L;
+            owner = q0 == 0 && lane / L < cnr;
         } else {
+            /* lane 4c owns row cfirst + c */
+            const int pc = lane >> 2;
+            myrow = cfirst + pc;
+            owner = (lane & 3) == 0 && pc < cnr;
             double acc = 0.0;
             int cur = 0;
             int nb = __shfl_sync(kFull, cv, 0);                  /* next row start relative to ccb, 256 = none */
@@ -428,11 +435,11 @@ cudaError_t sblas_launch_rowtile(const sblas_seg_args *a, int R, int window, cud
     if (dev >= 64 || R < 1 || R > 8) return cudaErrorInvalidValue;
     if (!attr_done[dev]) {
         cudaError_t e = cudaSuccess;
-#define RT_ATTR(NS) if (e == cudaSuccess) e = cudaFuncSetAttribute(spmv_rowtile_kernel<NS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmem); \
-                    if (e == cudaSuccess) e = cudaFuncSetAttribute(spmv_rowtile_kernel<NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmem); \
-                    if (e == cudaSuccess) e = cudaFuncSetAttribute(spmv_rowtile_kernel<NS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmem)
+#define RT_ATTR1(NS, RT) if (e == cudaSuccess) e = cudaFuncSetAttribute(spmv_rowtile_kernel<NS, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmem)
+#define RT_ATTR(NS) RT_ATTR1(NS, 0); RT_ATTR1(NS, 1); RT_ATTR1(NS, 2); RT_ATTR1(NS, 4); RT_ATTR1(NS, 8)
         RT_ATTR(4); RT_ATTR(5); RT_ATTR(6); RT_ATTR(7); RT_ATTR(8);
 #undef RT_ATTR
+#undef RT_ATTR1
         if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&g_rt_sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
@@ -447,6 +454,8 @@ cudaError_t sblas_launch_rowtile(const sblas_seg_args *a, int R, int window, cud
     if (window <= 0 || ns > 8) ns = 8;
 #define RT_LAUNCH(NS) do { if (R == 1) spmv_rowtile_kernel<NS, 1><<<grid, kRtThreads, kRtSmem, s>>>(*a, R); \
                            else if (R == 2) spmv_rowtile_kernel<NS, 2><<<grid, kRtThreads, kRtSmem, s>>>(*a, R); \
+                           else if (R == 4) spmv_rowtile_kernel<NS, 4><<<grid, kRtThreads, kRtSmem, s>>>(*a, R); \
+                           else if (R == 8) spmv_rowtile_kernel<NS, 8><<<grid, kRtThreads, kRtSmem, s>>>(*a, R); \
                            else spmv_rowtile_kernel<NS, 0><<<grid, kRtThreads, kRtSmem, s>>>(*a, R); } while (0)
     switch (ns) {
     case 1: case 2: case 3: case 4: RT_LAUNCH(4); break;

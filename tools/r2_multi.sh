@@ -1,11 +1,16 @@
 #!/bin/bash
-# usage: tools/r2_multi.sh N [steps]   (under gpurun --gpus N): GPU tests on N visible GPUs, then the bench at N.
+# usage: tools/r2_multi.sh N [steps]   (under gpurun --gpus N): the GPU tests that drive the reference entry points
+# IN-PROCESS over 1..N GPUs (SBLAS_EXPECT_GPUS=N: fewer visible GPUs is an error), then the bench at N (both arms).
 N=$1; STEPS=${2:-100}
 O=gpurun_out/r2m$N; mkdir -p $O
 nvidia-smi -L > $O/gpus.txt
-SBLAS_EXPECT_GPUS=$N timeout 1200 python -m pytest tests -m gpu -q > $O/pytest_gpu_n$N.log 2>&1; echo "pytest rc=$?"; tail -4 $O/pytest_gpu_n$N.log
-( time timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
-    bench.py --gpus $N --steps $STEPS --warmup 5 > $O/bench_n$N.json 2> $O/bench_n$N.err ) 2> $O/bench_n$N.time; echo "bench rc=$?"; tail -5 $O/bench_n$N.err; cat $O/bench_n$N.time
+( time SBLAS_EXPECT_GPUS=$N timeout 1200 python -m pytest tests -m gpu -q -x --durations=6 \
+    -k "qh768 or generator or versions_and_kernels or chained or byte_balanced or row_panels or row_tile or row_split or reference_code_live or spmm or sptrans or cli or spanning" \
+    > $O/pytest_gpu_n$N.log 2>&1 ) 2> $O/pytest.time; echo "pytest rc=$?"; tail -12 $O/pytest_gpu_n$N.log; tail -3 $O/pytest.time
+( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
+    bench.py --gpus $N --steps $STEPS --warmup 5 > $O/bench_n$N.json 2> $O/bench_n$N.err ) 2> $O/bench_n$N.time; echo "bench rc=$?"; tail -5 $O/bench_n$N.err; tail -3 $O/bench_n$N.time
+( timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 \
+    bench.py --impl reference --gpus $N --steps 5 --warmup 2 > $O/bench_ref_n$N.json 2> $O/bench_ref_n$N.err ); echo "ref rc=$?"; cut -c1-400 $O/bench_ref_n$N.json | tail -1
 python - $O/bench_n$N.json <<'PY'
 import json,sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
