@@ -51,6 +51,7 @@ typedef struct sblas_dev {
 
 struct sblas_spmv_plan {
     int version, m, n, kernel, q, world, rank, rank_mode, ndev, p2p, dry;
+    int x_policy;                     /* an L2 access-policy window over x is set on the streams (SBLAS_X_PERSIST=1) */
     long long nnz, nb;
     /* global partition, identical on every rank */
     int nparts; sblas_part *parts;

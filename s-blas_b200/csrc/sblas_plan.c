@@ -99,6 +99,35 @@ static void pick_kernel(int kernel, long long dev_nnz, int *kind, int *ipt)
     if (e == 4 || e == 8 || e == 16) *ipt = e;
 }
 
+/* Opt-in (SBLAS_X_PERSIST=1): an L2 access-policy window over the part of x the shard reads, persisting hits /
+ * streaming misses, on every stream of the GPU (the north star's "keep x in L2 via access-policy windows").
+ * The default instead marks the STREAMED arrays evict-first inside the kernels (sblas_dev_common.cuh), which needs no
+ * carve-out of the L2; DESIGN.md section 6 has the A/B.  Stream attributes are not captured into graph kernel
+ * nodes, so sblas_spmv_plan_step falls back to plain launches while the window is on. */
+static int apply_x_window_policy(sblas_spmv_plan *P, sblas_dev *D)
+{
+    if (!env_int("SBLAS_X_PERSIST", 0) || !D->d_x || D->col_hi < D->col_lo) return 0;
+    int max_win = 0, max_persist = 0;
+    if (cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, D->device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, D->device) != cudaSuccess ||
+        max_win <= 0 || max_persist <= 0) { cudaGetLastError(); return 0; }
+    size_t bytes = ((size_t)D->col_hi - D->col_lo + 1) * sizeof(double);
+    if (bytes > (size_t)max_win) bytes = (size_t)max_win;
+    size_t carve = bytes < (size_t)max_persist ? bytes : (size_t)max_persist;
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof av);
+    av.accessPolicyWindow.base_ptr = (void *)(D->d_x + D->col_lo);
+    av.accessPolicyWindow.num_bytes = bytes;
+    av.accessPolicyWindow.hitRatio = (float)((double)carve / (double)bytes);
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    for (int c = 0; c < D->nstreams; ++c)
+        if (cudaStreamSetAttribute(D->streams[c], cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) { cudaGetLastError(); return 0; }
+    P->x_policy = 1;
+    return 1;
+}
+
 /* ------------------------------------------------------------------ build */
 static void free_dev(sblas_dev *D, int dry)
 {
@@ -461,6 +490,8 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
             cudaFree(d_mm); d_mm = NULL;
             if (h_mm[0] >= 0 && h_mm[1] < P->n && h_mm[0] <= h_mm[1]) { D->col_lo = h_mm[0]; D->col_hi = h_mm[1]; }
         }
+
+        apply_x_window_policy(P, D);
 
         /* edge table: 2 doubles per local segment, device memory (peers read it over NVLink) */
         const int nl = D->seg_end - D->seg_begin;
@@ -1297,7 +1328,7 @@ int sblas_spmv_plan_step(sblas_spmv_plan *P, double alpha, double beta)
 {
     int rc = 0;
     const int exchange = P->rank_mode && P->world > 1 && P->peer_bound;
-    const int graphable = !P->dry && P->ndev == 1 && P->devs[0].seg_begin >= 0 && P->devs[0].nstreams == 1 &&
+    const int graphable = !P->dry && !P->x_policy && P->ndev == 1 && P->devs[0].seg_begin >= 0 && P->devs[0].nstreams == 1 &&
                           (P->rank_mode ? (P->world == 1 || exchange) : P->devs[0].nmerge >= 0) && env_int("SBLAS_GRAPH", 1);
     if (!graphable) {
         if ((rc = sblas_spmv_plan_execute_device(P, alpha, beta, 0)) != 0) return rc;
@@ -1367,6 +1398,7 @@ int sblas_spmv_plan_bind_peer_x(sblas_spmv_plan *P, void *const *peer_x, void *c
         D->d_x = (double *)peer_x[P->rank];
         for (int s = 0; s < P->nseg; ++s) P->segs[s].args.x = D->d_x;
         for (int u = 0; u < P->nunits; ++u) P->units[u].args.x = D->d_x;
+        apply_x_window_policy(P, D);
     }
     P->peer_x_bound = 1;
     P->graph_valid = 0;

@@ -103,7 +103,7 @@ def _worker(rank, world, port, version, nb, q, result_q):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("version,nb,q", [(sb.V1, 0, 1), (sb.V2, 7, 2), (sb.BASELINE, 0, 1)])
+@pytest.mark.parametrize("version,nb,q", [(sb.V1, 0, 1), (sb.V2, 7, 2), (sb.BASELINE, 0, 1), (sb.V1_BYTES, 0, 1)])
 def test_rank_sharded_spmv_over_gloo(world, version, nb, q):
     ctx = mp.get_context("spawn")
     result_q = ctx.SimpleQueue()

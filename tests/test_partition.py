@@ -142,3 +142,35 @@ def test_byte_balanced_partition_properties():
                 w = 12.0 * (e + 1 - s) + 28.0 * (r1 - r0)
                 assert abs(w - share) <= 12.0 * lens.max() + 56.0, (g, i, w, share)
                 assert p["start_row"][i] == sb.get_row_from_index(m, rp, s) and p["end_row"][i] == sb.get_row_from_index(m, rp, e)
+
+
+def test_partitions_bit_exact_on_the_full_size_row_pointers():
+    """The partitioners on the row pointers of the BASELINE configs themselves (config 2b: 1 M rows / 1.2125 G
+    entries; config 5: 50 M rows / 1.2125 G entries; config 3: the power-law row lengths), not only on qh768-sized
+    inputs: int64 arithmetic near 2^31 per shard, 50 M-entry bisections."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    for name in ("g1m", "big50m", "circuit5m"):
+        lens = bench.workload(name)["row_len"]()
+        rp = np.zeros(len(lens) + 1, np.int64)
+        np.cumsum(lens, out=rp[1:])
+        nnz = int(rp[-1])
+        for ngpu in (1, 2, 4, 8):
+            a, b = sb.partition_v1(rp, ngpu), oracle.partition_v1(rp, ngpu)
+            for k in KEYS:
+                assert (a[k] == b[k]).all(), (name, "v1", k, ngpu)
+            a, b = sb.partition_baseline(rp, ngpu), oracle.partition_baseline(rp, ngpu)
+            for k in ("start_row", "end_row", "dev_m", "dev_nnz"):
+                assert (a[k] == b[k]).all(), (name, "baseline", k, ngpu)
+            nb = nnz // (ngpu * 8)                               # the harness's d = ngpu, c = 8 sweep point
+            a, b = sb.generate_tasks_v2(rp, nb), oracle.generate_tasks_v2(rp, nb)
+            for k in KEYS:
+                assert (a[k] == b[k]).all(), (name, "v2", k, ngpu)
+        # the reference's own compiled row lookup on the shard borders of the 8-way split
+        ref = oracle.ref_helper()
+        if ref is not None:
+            p8 = sb.partition_v1(rp, 8)
+            for i in range(8):
+                for idx in (int(p8["start_idx"][i]), int(p8["end_idx"][i])):
+                    assert ref(len(rp) - 1, rp, idx) == sb.get_row_from_index(len(rp) - 1, rp, idx), (name, idx)
