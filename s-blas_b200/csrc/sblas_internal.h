@@ -30,12 +30,18 @@ typedef struct sblas_dev {
     int first_row, last_row, rows, nnz;
     double *d_val; int *d_col; int own_matrix;
     int *d_rowptr; double *d_x; double *d_y;
-    long long *stage64;               /* plan build: the int64 row pointer slice on its way to d_rowptr */
-    double *d_edge; int edge_is_host, edge_bound; void *h_edge_alloc;
+    long long *stage64;               /* plan build: the int64 row pointer slice on its way to d_rowptr (aliases d_y) */
+    double *d_edge; int edge_bound;
     double *d_carry, *d_tail; int *d_tstart, *d_tmeta;
     /* merge lists of the split rows this GPU owns */
     int nmerge, nmsrc;
     int *d_mrow, *d_mbeg; const double **d_msrc;
+    /* the arrays above are carved out of three allocations (cudaMalloc/cudaFree with peer access enabled map into
+     * every GPU's address space: their count, not their size, is what a one-shot call pays for) */
+    char *slab_main;                  /* val, col (when owned), rowptr, x, y, edge table, column-range scratch */
+    char *slab_tiles;                 /* tmeta, tstart, carry, tail */
+    char *slab_merge;                 /* mrow, mbeg, msrc */
+    int *d_mm;                        /* plan build: {min, max} column of the shard */
     int *h_mrow, *h_mbeg; const double **h_msrc; long long *h_msrc_off;
     cudaStream_t *streams; int nstreams;
     cudaEvent_t *ev_seg, ev_in, ev_done;

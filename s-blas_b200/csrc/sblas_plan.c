@@ -136,11 +136,7 @@ static void free_dev(sblas_dev *D, int dry)
         return;
     }
     if (D->device >= 0) cudaSetDevice(D->device);
-    if (D->own_matrix) { cudaFree(D->d_val); cudaFree(D->d_col); }
-    cudaFree(D->d_rowptr); cudaFree(D->d_x); cudaFree(D->d_y);
-    if (D->edge_is_host) cudaFreeHost(D->h_edge_alloc); else if (!D->edge_bound) cudaFree(D->d_edge);
-    cudaFree(D->d_carry); cudaFree(D->d_tail); cudaFree(D->d_tstart); cudaFree(D->d_tmeta);
-    cudaFree(D->d_mrow); cudaFree(D->d_mbeg); cudaFree(D->d_msrc);
+    cudaFree(D->slab_main); cudaFree(D->slab_tiles); cudaFree(D->slab_merge);   /* every device array lives in these */
     if (D->streams) {
         for (int c = 0; c < D->nstreams; ++c) {
             if (D->streams[c]) cudaStreamDestroy(D->streams[c]);
@@ -163,6 +159,7 @@ static void free_dev(sblas_dev *D, int dry)
 void sblas_spmv_plan_destroy(sblas_spmv_plan *P)
 {
     if (!P) return;
+    const double t_destroy = getenv("SBLAS_TIMING") ? sblas_get_time() : 0.0;
     if (P->x_alloc) { P->devs[0].d_x = P->x_alloc; P->x_alloc = NULL; }   /* the bound peer x is the caller's: free our own */
     for (int d = 0; d < P->ndev; ++d) free_dev(&P->devs[d], P->dry);
     if (P->peer_bound) {
@@ -176,6 +173,7 @@ void sblas_spmv_plan_destroy(sblas_spmv_plan *P)
     free(P->g_lo); free(P->g_hi); free(P->g_sf); free(P->g_sl);
     free(P->piece_lo); free(P->piece_hi); free(P->piece_unit);
     free(P);
+    if (t_destroy > 0.0) fprintf(stderr, "sblas plan destroy: %.3f ms\n", (sblas_get_time() - t_destroy) * 1e3);
 }
 
 /* Global segment table (every GPU / rank computes the same one): reference
@@ -349,9 +347,14 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
 {
     int rc = 0;
     int *d_stats = NULL, *h_stats = NULL, stats_cap = 0;      /* row-block statistics scratch */
-    int *d_mm = NULL;                                         /* column range scratch */
     const int dry = (src_flags & SBLAS_LAYOUT_ONLY) != 0;     /* host layout only: no CUDA call at all */
     P->dry = dry;
+    /* SBLAS_TIMING: where a plan build spends its wall time (stderr, one line per plan) */
+    const int timing = getenv("SBLAS_TIMING") != NULL;
+    double tm[8] = {0};
+    int ntm = 0;
+#define STAMP() do { if (timing && ntm < 8) tm[ntm++] = sblas_get_time(); } while (0)
+    STAMP();
     if (build_global(P, rp) != 0) { sblas_set_error("%s%s (line %d)", "partition failed", "", __LINE__); return -1; }
 
     /* ---- local segments per GPU */
@@ -444,28 +447,45 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
         cudaStream_t st = D->streams[0];
         (void)st;
 
-        if (src_flags & SBLAS_SRC_DEVICE_SHARD) {
-            D->d_val = (double *)val; D->d_col = (int *)col; D->own_matrix = 0;
-        } else {
-            D->own_matrix = 1;
-            /* +16: bulk copies round the last tile up to 16 bytes */
-            CU(cudaMalloc((void **)&D->d_val, ((size_t)D->nnz + 16) * sizeof(double)));
-            CU(cudaMalloc((void **)&D->d_col, ((size_t)D->nnz + 16) * sizeof(int)));
+        /* one allocation for everything whose size is known now, each array on a 256-byte boundary */
+        D->own_matrix = !(src_flags & SBLAS_SRC_DEVICE_SHARD);
+        const size_t nedge = (size_t)(2 * (P->rank_mode ? P->max_local : D->seg_end - D->seg_begin) + 2);
+        size_t off = 0;
+#define SLOT(bytes) (off = (off + 255) & ~(size_t)255, off += (size_t)(bytes), off - (size_t)(bytes))
+        /* +16: bulk copies round the last tile up to 16 bytes */
+        const size_t o_val = D->own_matrix ? SLOT(((size_t)D->nnz + 16) * sizeof(double)) : 0;
+        const size_t o_col = D->own_matrix ? SLOT(((size_t)D->nnz + 16) * sizeof(int)) : 0;
+        const size_t o_rp = SLOT(((size_t)D->rows + 1 + 8) * sizeof(int));
+        const size_t o_x = SLOT((size_t)(P->n > 0 ? P->n : 1) * sizeof(double));
+        const size_t o_y = SLOT(((size_t)D->rows + 2) * sizeof(double));      /* doubles as the int64 row pointer stage */
+        const size_t o_edge = SLOT(nedge * sizeof(double));
+        const size_t o_mm = SLOT(2 * sizeof(int));
+#undef SLOT
+        CU(cudaMalloc((void **)&D->slab_main, off));
+        if (D->own_matrix) {
+            D->d_val = (double *)(D->slab_main + o_val); D->d_col = (int *)(D->slab_main + o_col);
             if (D->nnz > 0) {
                 CU(cudaMemcpyAsync(D->d_val, val + D->first_idx, (size_t)D->nnz * sizeof(double), cudaMemcpyHostToDevice, st));
                 CU(cudaMemcpyAsync(D->d_col, col + D->first_idx, (size_t)D->nnz * sizeof(int), cudaMemcpyHostToDevice, st));
             }
+        } else {
+            D->d_val = (double *)val; D->d_col = (int *)col;
         }
-        CU(cudaMalloc((void **)&D->d_rowptr, ((size_t)D->rows + 1 + 8) * sizeof(int)));
+        D->d_rowptr = (int *)(D->slab_main + o_rp);
+        D->d_x = (double *)(D->slab_main + o_x);
+        D->d_y = (double *)(D->slab_main + o_y);
+        D->d_edge = (double *)(D->slab_main + o_edge);      /* 2 doubles per local segment (peers read it over NVLink) */
+        D->d_mm = (int *)(D->slab_main + o_mm);
         CU(cudaMemsetAsync(D->d_rowptr, 0, ((size_t)D->rows + 1 + 8) * sizeof(int), st));
-        CU(cudaMalloc((void **)&D->d_x, (size_t)(P->n > 0 ? P->n : 1) * sizeof(double)));
-        CU(cudaMalloc((void **)&D->d_y, (size_t)(D->rows > 0 ? D->rows : 1) * sizeof(double)));
-        /* int64 host row pointer slice -> int32 rebased/clamped, on the GPU */
-        CU(cudaMalloc((void **)&D->stage64, (size_t)(D->rows + 1) * sizeof(long long)));
+        CU(cudaMemsetAsync(D->d_edge, 0, nedge * sizeof(double), st));
+        /* int64 host row pointer slice -> int32 rebased/clamped, on the GPU; staged in y's storage, which nothing
+         * touches before the first product */
+        D->stage64 = (long long *)D->d_y;
         CU(cudaMemcpyAsync(D->stage64, rp + D->first_row, (size_t)(D->rows + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
         CU(sblas_launch_rebase_rowptr(D->stage64, D->first_idx, D->nnz, (long long)D->rows + 1, D->d_rowptr, st));
         }   /* !dry */
     }
+    STAMP();                                                   /* [1] partition, allocations, uploads enqueued */
 
     /* ---- second pass per GPU (the uploads of ALL GPUs are in flight by now, each over its own PCIe link):
      * wait for this GPU's shard, then column window, panels, tile metadata */
@@ -476,27 +496,21 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
         CU(cudaSetDevice(D->device));
         cudaStream_t st = D->streams[0];
         CU(cudaStreamSynchronize(st));
-        CU(cudaFree(D->stage64)); D->stage64 = NULL;
+        D->stage64 = NULL;
 
         /* the window of x this shard reads: [col_lo, col_hi] (one reduction over col at plan time) */
         D->col_lo = 0; D->col_hi = P->n - 1;
         if (D->nnz > 0 && env_int("SBLAS_X_WINDOW", 1)) {
             int h_mm[2] = {0x7fffffff, -1};
-            CU(cudaMalloc((void **)&d_mm, 2 * sizeof(int)));
-            CU(cudaMemcpyAsync(d_mm, h_mm, sizeof h_mm, cudaMemcpyHostToDevice, st));
-            CU(sblas_launch_col_range(D->d_col, D->nnz, d_mm, st));
-            CU(cudaMemcpyAsync(h_mm, d_mm, sizeof h_mm, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(D->d_mm, h_mm, sizeof h_mm, cudaMemcpyHostToDevice, st));
+            CU(sblas_launch_col_range(D->d_col, D->nnz, D->d_mm, st));
+            CU(cudaMemcpyAsync(h_mm, D->d_mm, sizeof h_mm, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
-            cudaFree(d_mm); d_mm = NULL;
             if (h_mm[0] >= 0 && h_mm[1] < P->n && h_mm[0] <= h_mm[1]) { D->col_lo = h_mm[0]; D->col_hi = h_mm[1]; }
         }
 
         apply_x_window_policy(P, D);
 
-        /* edge table: 2 doubles per local segment, device memory (peers read it over NVLink) */
-        const int nl = D->seg_end - D->seg_begin;
-        CU(cudaMalloc((void **)&D->d_edge, (size_t)(2 * (P->rank_mode ? P->max_local : nl) + 2) * sizeof(double)));
-        CU(cudaMemsetAsync(D->d_edge, 0, (size_t)(2 * (P->rank_mode ? P->max_local : nl) + 2) * sizeof(double), st));
         }   /* !dry */
 
         /* ---- segments: kernel choice, panels, tiles */
@@ -605,10 +619,12 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
         if (dry) continue;
         cudaStream_t st = D->streams[0];
         if (tiles_total > 0) {
-            CU(cudaMalloc((void **)&D->d_tmeta, (size_t)(tiles_total + 1) * 8 * sizeof(int)));
-            CU(cudaMalloc((void **)&D->d_tstart, (size_t)(tiles_total + 1) * sizeof(int)));
-            CU(cudaMalloc((void **)&D->d_carry, (size_t)(tiles_total + 1) * sizeof(double)));
-            CU(cudaMalloc((void **)&D->d_tail, (size_t)(tiles_total + 1) * sizeof(double)));
+            const size_t nt = (((size_t)tiles_total + 1) + 31) & ~(size_t)31;      /* keeps every array 256-byte aligned */
+            CU(cudaMalloc((void **)&D->slab_tiles, nt * (8 * sizeof(int) + sizeof(int) + 2 * sizeof(double))));
+            D->d_tmeta = (int *)D->slab_tiles;
+            D->d_carry = (double *)(D->slab_tiles + nt * 8 * sizeof(int));
+            D->d_tail = D->d_carry + nt;
+            D->d_tstart = (int *)(D->d_tail + nt);
         }
         for (int s = D->seg_begin; s < D->seg_end; ++s) {
             for (int ui = P->segs[s].unit_begin; ui < P->segs[s].unit_end; ++ui) {
@@ -629,6 +645,7 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
         CU(cudaStreamSynchronize(st));
     }
 
+    STAMP();                                                   /* [2] uploads landed, panels, tile metadata */
     /* ---- peer access between the GPUs of an in-process plan */
     P->p2p = 0;
     if (!dry && !P->rank_mode && ndev > 1) {
@@ -657,6 +674,7 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
         }
     }
 
+    STAMP();                                                   /* [3] peer access */
     /* ---- merge lists: one entry per split row, on the GPU that owns the row's start.
      * Sources are listed in ascending global segment order (deterministic sum). */
     for (int d = 0; d < ndev; ++d) {
@@ -703,20 +721,27 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
         D->h_mbeg[nrow] = nsrc;
         if (nrow > 0 && !dry) {
             CU(cudaSetDevice(D->device));
-            CU(cudaMalloc((void **)&D->d_mrow, (size_t)nrow * sizeof(int)));
-            CU(cudaMalloc((void **)&D->d_mbeg, (size_t)(nrow + 1) * sizeof(int)));
-            CU(cudaMalloc((void **)&D->d_msrc, (size_t)nsrc * sizeof(double *)));
+            const size_t o_beg = (((size_t)nsrc * sizeof(double *)) + 255) & ~(size_t)255;
+            const size_t o_row = (o_beg + ((size_t)nrow + 1) * sizeof(int) + 255) & ~(size_t)255;
+            CU(cudaMalloc((void **)&D->slab_merge, o_row + (size_t)nrow * sizeof(int)));
+            D->d_msrc = (const double **)D->slab_merge;
+            D->d_mbeg = (int *)(D->slab_merge + o_beg);
+            D->d_mrow = (int *)(D->slab_merge + o_row);
             CU(cudaMemcpy(D->d_mrow, D->h_mrow, (size_t)nrow * sizeof(int), cudaMemcpyHostToDevice));
             CU(cudaMemcpy(D->d_mbeg, D->h_mbeg, (size_t)(nrow + 1) * sizeof(int), cudaMemcpyHostToDevice));
             if (!P->rank_mode)
                 CU(cudaMemcpy(D->d_msrc, D->h_msrc, (size_t)nsrc * sizeof(double *), cudaMemcpyHostToDevice));
         }
     }
+    STAMP();                                                   /* [4] merge lists */
+    if (timing && ntm == 5)
+        fprintf(stderr, "sblas plan build (%d GPU%s): alloc+enqueue %.3f ms, upload wait+panels+tiles %.3f ms, peer access %.3f ms, "
+                "merge lists %.3f ms\n", ndev, ndev > 1 ? "s" : "", (tm[1] - tm[0]) * 1e3, (tm[2] - tm[1]) * 1e3,
+                (tm[3] - tm[2]) * 1e3, (tm[4] - tm[3]) * 1e3);
+#undef STAMP
     return 0;
 fail:
-    for (int d = 0; d < P->ndev; ++d) if (P->devs[d].stage64) { cudaFree(P->devs[d].stage64); P->devs[d].stage64 = NULL; }
     if (d_stats) cudaFree(d_stats);
-    if (d_mm) cudaFree(d_mm);
     free(h_stats);
     return rc;
 }
@@ -1412,8 +1437,7 @@ int sblas_spmv_plan_bind_edge_table(sblas_spmv_plan *P, double *device_block)
     sblas_dev *D = &P->devs[0];
     if (D->seg_begin < 0) return 0;
     cudaSetDevice(D->device);
-    if (!D->edge_is_host && !D->edge_bound) cudaFree(D->d_edge);
-    D->d_edge = device_block;
+    D->d_edge = device_block;                 /* the plan's own table stays inside its allocation, unused */
     D->edge_bound = 1;
     for (int s = D->seg_begin; s < D->seg_end; ++s) P->segs[s].args.edge = D->d_edge + 2 * P->segs[s].lidx;
     return 0;
