@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include "sblas_internal.h"
 #include "sblas_spmv.h"
 #include "spmv_kernel.h"
 
@@ -46,6 +47,7 @@ void sblas_spmv_cache_clear(void)
         if (g_cache[i].plan) sblas_spmv_plan_destroy(g_cache[i].plan);
         memset(&g_cache[i], 0, sizeof g_cache[i]);
     }
+    sblas_pool_release();
 }
 
 static int one_shot(int version, int m, int n, long long nnz, double *alpha, double *val, long long *rp,
@@ -78,7 +80,9 @@ static int one_shot(int version, int m, int n, long long nnz, double *alpha, dou
     sblas_spmv_plan *plan = NULL;
     const int timing = getenv("SBLAS_TIMING") != NULL;
     const double t0 = timing ? sblas_get_time() : 0.0;
-    int rc = sblas_spmv_plan_create(&plan, version, m, n, nnz, val, rp, col, ngpu, kernel, nb, q);
+    const char *pe = getenv("SBLAS_POOL");
+    const int pooled = (pe && *pe == '0') ? 0 : SBLAS_CREATE_POOLED;
+    int rc = sblas_spmv_plan_create_flags(&plan, version, m, n, nnz, val, rp, col, ngpu, kernel, nb, q, pooled);
     if (rc != 0) {
         if (getenv("SBLAS_VERBOSE")) fprintf(stderr, "sblas: %s\n", sblas_last_error());
         return rc;

@@ -39,6 +39,7 @@ typedef struct sblas_dev {
     /* the arrays above are carved out of three allocations (cudaMalloc/cudaFree with peer access enabled map into
      * every GPU's address space: their count, not their size, is what a one-shot call pays for) */
     char *slab_main;                  /* val, col (when owned), rowptr, x, y, edge table, column-range scratch */
+    size_t slab_main_bytes;
     char *slab_tiles;                 /* tmeta, tstart, carry, tail */
     char *slab_merge;                 /* mrow, mbeg, msrc */
     int *d_mm;                        /* plan build: {min, max} column of the shard */
@@ -58,6 +59,7 @@ typedef struct sblas_dev {
 struct sblas_spmv_plan {
     int version, m, n, kernel, q, world, rank, rank_mode, ndev, p2p, dry;
     int x_policy;                     /* an L2 access-policy window over x is set on the streams (SBLAS_X_PERSIST=1) */
+    int pooled;                       /* main allocations come from / go back to the per-GPU pool (one-shot calls) */
     long long nnz, nb;
     /* global partition, identical on every rank */
     int nparts; sblas_part *parts;
@@ -81,4 +83,14 @@ struct sblas_spmv_plan {
 };
 
 void sblas_set_error(const char *fmt, const char *a, const char *b, int line);
+
+/* One retained main allocation per GPU for the one-shot entry points (sblas_api.c): with peer access enabled a
+ * cudaMalloc + cudaFree pair of a GB-sized shard costs tens of ms, far more than the product, and the reference's
+ * harness calls the one-shot entry points again and again.  SBLAS_POOL=0 turns it off;
+ * sblas_spmv_cache_clear() gives the memory back. */
+#define SBLAS_CREATE_POOLED 0x100
+int sblas_spmv_plan_create_flags(sblas_spmv_plan **plan, int version, int m, int n, long long nnz,
+                                 const double *csrVal, const long long *csrRowPtr, const int *csrColIndex,
+                                 int ngpu, int kernel, long long nb, int q, int flags);
+void sblas_pool_release(void);
 #endif

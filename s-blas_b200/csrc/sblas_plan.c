@@ -16,6 +16,7 @@
  * There is no CPU arithmetic on this path and no CPU fallback.
  */
 #include <cuda_runtime_api.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -128,15 +129,86 @@ static int apply_x_window_policy(sblas_spmv_plan *P, sblas_dev *D)
     return 1;
 }
 
+/* ------------------------------------------------------------------ per-GPU pool of main allocations */
+#define SBLAS_POOL_DEVS 64
+static struct { char *ptr; size_t bytes; } g_pool[SBLAS_POOL_DEVS];
+static pthread_mutex_t g_pool_mu = PTHREAD_MUTEX_INITIALIZER;
+
+static size_t pool_bytes(int device)
+{
+    size_t b = 0;
+    if (device >= 0 && device < SBLAS_POOL_DEVS) {
+        pthread_mutex_lock(&g_pool_mu);
+        b = g_pool[device].ptr ? g_pool[device].bytes : 0;
+        pthread_mutex_unlock(&g_pool_mu);
+    }
+    return b;
+}
+
+/* the current device is `device`; *got = the size of the block handed out (>= need) */
+static cudaError_t slab_get(int device, size_t need, int pooled, char **out, size_t *got)
+{
+    if (pooled && device >= 0 && device < SBLAS_POOL_DEVS) {
+        char *old = NULL;
+        pthread_mutex_lock(&g_pool_mu);
+        if (g_pool[device].ptr && g_pool[device].bytes >= need) {
+            *out = g_pool[device].ptr; *got = g_pool[device].bytes;
+            g_pool[device].ptr = NULL; g_pool[device].bytes = 0;
+            pthread_mutex_unlock(&g_pool_mu);
+            return cudaSuccess;
+        }
+        old = g_pool[device].ptr;                              /* too small: make room before asking for more */
+        g_pool[device].ptr = NULL; g_pool[device].bytes = 0;
+        pthread_mutex_unlock(&g_pool_mu);
+        if (old) cudaFree(old);
+    }
+    *got = need;
+    return cudaMalloc((void **)out, need);
+}
+
+/* the current device is `device` and nothing is in flight on the block */
+static void slab_put(int device, char *ptr, size_t bytes, int pooled)
+{
+    if (!ptr) return;
+    if (pooled && device >= 0 && device < SBLAS_POOL_DEVS) {
+        pthread_mutex_lock(&g_pool_mu);
+        if (!g_pool[device].ptr || g_pool[device].bytes < bytes) {   /* keep the larger of the two */
+            char *t = g_pool[device].ptr;
+            g_pool[device].ptr = ptr; g_pool[device].bytes = bytes;
+            ptr = t;
+        }
+        pthread_mutex_unlock(&g_pool_mu);
+    }
+    if (ptr) cudaFree(ptr);
+}
+
+void sblas_pool_release(void)
+{
+    int cur = 0;
+    const int have = cudaGetDevice(&cur) == cudaSuccess;
+    for (int d = 0; d < SBLAS_POOL_DEVS; ++d) {
+        pthread_mutex_lock(&g_pool_mu);
+        char *p = g_pool[d].ptr;
+        g_pool[d].ptr = NULL; g_pool[d].bytes = 0;
+        pthread_mutex_unlock(&g_pool_mu);
+        if (p && cudaSetDevice(d) == cudaSuccess) cudaFree(p);
+    }
+    if (have) cudaSetDevice(cur); else cudaGetLastError();
+}
+
 /* ------------------------------------------------------------------ build */
-static void free_dev(sblas_dev *D, int dry)
+static void free_dev(sblas_dev *D, int dry, int pooled)
 {
     if (dry) {
         free(D->h_mrow); free(D->h_mbeg); free(D->h_msrc); free(D->h_msrc_off);
         return;
     }
     if (D->device >= 0) cudaSetDevice(D->device);
-    cudaFree(D->slab_main); cudaFree(D->slab_tiles); cudaFree(D->slab_merge);   /* every device array lives in these */
+    /* every device array lives in these three */
+    if (pooled && D->slab_main) cudaDeviceSynchronize();      /* the next plan writes into the block straight away */
+    slab_put(D->device, D->slab_main, D->slab_main_bytes, pooled);
+    D->slab_main = NULL;
+    cudaFree(D->slab_tiles); cudaFree(D->slab_merge);
     if (D->streams) {
         for (int c = 0; c < D->nstreams; ++c) {
             if (D->streams[c]) cudaStreamDestroy(D->streams[c]);
@@ -161,7 +233,7 @@ void sblas_spmv_plan_destroy(sblas_spmv_plan *P)
     if (!P) return;
     const double t_destroy = getenv("SBLAS_TIMING") ? sblas_get_time() : 0.0;
     if (P->x_alloc) { P->devs[0].d_x = P->x_alloc; P->x_alloc = NULL; }   /* the bound peer x is the caller's: free our own */
-    for (int d = 0; d < P->ndev; ++d) free_dev(&P->devs[d], P->dry);
+    for (int d = 0; d < P->ndev; ++d) free_dev(&P->devs[d], P->dry, P->pooled);
     if (P->peer_bound) {
         cudaFree(P->d_peer_bases); cudaFree(P->d_out_slot); cudaFree(P->d_out_owner); cudaFree(P->d_out_off);
         cudaFree(P->d_owners); cudaFree(P->d_contrib); cudaFree(P->d_msrc_off); cudaFree(P->d_epoch);
@@ -425,6 +497,7 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
         {
             size_t fr = 0, tot = 0;
             CU(cudaMemGetInfo(&fr, &tot));
+            fr += pool_bytes(D->device);                       /* the retained block is ours to reuse */
             const double need = 12.0 * D->nnz * ((src_flags & SBLAS_SRC_DEVICE_SHARD) ? 0.0 : 1.0) +
                                 4.0 * (D->rows + 1) + 8.0 * P->n + 8.0 * D->rows;
             if (need / 1e9 > 0.8 * ((double)fr / 1e9)) {
@@ -461,7 +534,7 @@ static int plan_build(sblas_spmv_plan *P, const double *val, const long long *rp
         const size_t o_edge = SLOT(nedge * sizeof(double));
         const size_t o_mm = SLOT(2 * sizeof(int));
 #undef SLOT
-        CU(cudaMalloc((void **)&D->slab_main, off));
+        CU(slab_get(D->device, off, P->pooled, &D->slab_main, &D->slab_main_bytes));
         if (D->own_matrix) {
             D->d_val = (double *)(D->slab_main + o_val); D->d_col = (int *)(D->slab_main + o_col);
             if (D->nnz > 0) {
@@ -781,6 +854,13 @@ int sblas_spmv_plan_create(sblas_spmv_plan **plan, int version, int m, int n, lo
                            const double *csrVal, const long long *csrRowPtr, const int *csrColIndex,
                            int ngpu, int kernel, long long nb, int q)
 {
+    return sblas_spmv_plan_create_flags(plan, version, m, n, nnz, csrVal, csrRowPtr, csrColIndex, ngpu, kernel, nb, q, 0);
+}
+
+int sblas_spmv_plan_create_flags(sblas_spmv_plan **plan, int version, int m, int n, long long nnz,
+                                 const double *csrVal, const long long *csrRowPtr, const int *csrColIndex,
+                                 int ngpu, int kernel, long long nb, int q, int flags)
+{
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count < ngpu || ngpu <= 0) {
         cudaGetLastError();
@@ -794,6 +874,7 @@ int sblas_spmv_plan_create(sblas_spmv_plan **plan, int version, int m, int n, lo
     if (ngpu > 64) { sblas_spmv_plan_destroy(*plan); *plan = NULL; return -1; }
     for (int d = 0; d < ngpu; ++d) devices[d] = d;
     (*plan)->rank_mode = 0;
+    (*plan)->pooled = (flags & SBLAS_CREATE_POOLED) != 0;
     rc = plan_build(*plan, csrVal, csrRowPtr, csrColIndex, devices, SBLAS_SRC_HOST);
     if (rc) { sblas_spmv_plan_destroy(*plan); *plan = NULL; }
     return rc;

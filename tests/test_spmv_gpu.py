@@ -433,6 +433,43 @@ def test_one_shot_plan_cache(qh768, monkeypatch):
     sb.cache_clear()
 
 
+def test_one_shot_calls_reuse_a_retained_allocation(monkeypatch):
+    """The one-shot entry points keep one main allocation per GPU between calls (a cudaMalloc + cudaFree pair of a
+    shard costs more than the product once peer access is on).  Matrices of growing and shrinking size, every version
+    and GPU count, must give bit-for-bit what the same calls give with the pool off (SBLAS_POOL=0); cache_clear()
+    hands the memory back."""
+    import torch
+    r, c, v, _, _ = oracle.gen_g(200)              # warm call: kernels loaded before free memory is read
+    y = np.zeros(200)
+    assert sb.spMV_mgpu_v1(200, 200, len(v), A, v, oracle.coo_to_rowptr(200, r), c, np.ones(200), B, y, 1, 1) == 0
+    sb.cache_clear()
+    free0 = torch.cuda.mem_get_info(0)[0]
+    results = {}
+    for pool in ("1", "0"):
+        monkeypatch.setenv("SBLAS_POOL", pool)
+        for idx, n in enumerate((3000, 200, 9000, 56, 9000, 1200)):          # up, down, up, tiny, same again, mid
+            r, c, v, _, _ = oracle.gen_g(n)
+            rp = oracle.coo_to_rowptr(n, r)
+            rs = np.random.default_rng(1000 + idx)
+            x, y0 = rs.standard_normal(n), rs.standard_normal(n)
+            for g in gpu_counts():
+                for name, fn, extra in (("v1", sb.spMV_mgpu_v1, (g, 1)), ("v2", sb.spMV_mgpu_v2, (g, 1, max(1, len(v) // (3 * g)), 2)),
+                                        ("base", sb.spMV_mgpu_baseline, (g,))):
+                    y = y0.copy()
+                    assert fn(n, n, len(v), A, v, rp, c, x, B, y, *extra) == 0, sb.last_error()
+                    if pool == "1":
+                        check_tol(y, oracle.csr_spmv(rp, c, v, x, A, B, y0), oracle.csr_spmv_bound(rp, c, v, x, A, B, y0),
+                                  "pool n=%d g=%d %s" % (n, g, name))
+                        results[(idx, g, name)] = y
+                    else:
+                        assert (y == results[(idx, g, name)]).all(), ("pooled and unpooled differ", n, g, name)
+        if pool == "1":
+            held = free0 - torch.cuda.mem_get_info(0)[0]
+            assert held > 0, "the pool should be holding GPU 0's block"
+            sb.cache_clear()
+            assert torch.cuda.mem_get_info(0)[0] >= free0 - (8 << 20), "cache_clear() must give the block back"
+
+
 def test_against_cusparse_generic_spmv(qh768):
     """Third opinion on the arithmetic: the reference's csrmv is legacy cuSPARSE (removed in CUDA 11);
     its living successor, the generic cusparseSpMV that torch's sparse CSR mat-vec calls, must agree
