@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(kRtThreads, 2) spmv_rowtile_kernel(const sblas
     }
 }
 
-/* Off by default (SBLAS_MEDIUM bit 1) until it has been measured and tested as widely as the others.
+/* On by default since round 2 (SBLAS_MEDIUM bit 1; SBLAS_MEDIUM=1 turns these panels off).
  * Rows of 257 .. 2048 entries: G = 2, 4 or 8 warps per row (every row of the panel holds at most 256*G
  * entries), a tile is 8/G whole rows.  Warp w takes part w % G of row w / G (the row cut into G equal
  * pieces of at most 256 entries), reduces it like the R == 1 case above and posts one partial sum; after
