@@ -1029,10 +1029,14 @@ int sblas_spmv_plan_upload(sblas_spmv_plan *P, const double *x, const double *y)
             for (int o = 0; o < nd; ++o) {
                 sblas_dev *O = &P->devs[o];
                 if (o == d || O->seg_begin < 0 || O->xs_hi <= O->xs_lo) continue;
-                /* pull O's slice once it has landed there */
+                /* pull O's slice once it has landed there -- only the part inside the window of columns D's
+                 * shard reads (a banded matrix on 8 GPUs needs about an eighth of x per GPU) */
+                const long long lo = O->xs_lo > D->col_lo ? O->xs_lo : D->col_lo;
+                const long long hi = O->xs_hi < (long long)D->col_hi + 1 ? O->xs_hi : (long long)D->col_hi + 1;
+                if (hi <= lo) continue;
                 CU(cudaStreamWaitEvent(D->streams[0], O->ev_in, 0));
-                CU(cudaMemcpyPeerAsync(D->d_x + O->xs_lo, D->device, O->d_x + O->xs_lo, O->device,
-                                       (size_t)(O->xs_hi - O->xs_lo) * sizeof(double), D->streams[0]));
+                CU(cudaMemcpyPeerAsync(D->d_x + lo, D->device, O->d_x + lo, O->device,
+                                       (size_t)(hi - lo) * sizeof(double), D->streams[0]));
             }
             CU(cudaEventRecord(D->ev_xpull, D->streams[0]));     /* the next upload on every peer waits for this */
             D->xpull_recorded = 1;
