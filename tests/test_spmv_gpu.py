@@ -443,7 +443,6 @@ def test_one_shot_calls_reuse_a_retained_allocation(monkeypatch):
     y = np.zeros(200)
     assert sb.spMV_mgpu_v1(200, 200, len(v), A, v, oracle.coo_to_rowptr(200, r), c, np.ones(200), B, y, 1, 1) == 0
     sb.cache_clear()
-    free0 = torch.cuda.mem_get_info(0)[0]
     results = {}
     for pool in ("1", "0"):
         monkeypatch.setenv("SBLAS_POOL", pool)
@@ -464,10 +463,10 @@ def test_one_shot_calls_reuse_a_retained_allocation(monkeypatch):
                     else:
                         assert (y == results[(idx, g, name)]).all(), ("pooled and unpooled differ", n, g, name)
         if pool == "1":
-            held = free0 - torch.cuda.mem_get_info(0)[0]
-            assert held > 0, "the pool should be holding GPU 0's block"
+            free_pooled = torch.cuda.mem_get_info(0)[0]
             sb.cache_clear()
-            assert torch.cuda.mem_get_info(0)[0] >= free0 - (8 << 20), "cache_clear() must give the block back"
+            # GPU 0's retained block is the one-GPU shard of the 9,000-row matrix (9.8 M entries x 12 B = 118 MB)
+            assert torch.cuda.mem_get_info(0)[0] - free_pooled >= (100 << 20), "cache_clear() must give the block back"
 
 
 def test_against_cusparse_generic_spmv(qh768):
