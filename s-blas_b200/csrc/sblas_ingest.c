@@ -85,6 +85,8 @@ int sblas_mtx_read_csr(const char *path, long long *rp, int *col, double *val)
     mtx_head h;
     int rc = read_head(f, &h);
     if (rc != 0) { fclose(f); return rc; }
+    /* untrusted size line: an entry count whose byte size wraps size_t would turn into a short allocation */
+    if ((unsigned long long)h.listed > (unsigned long long)((size_t)-1) / (4 * sizeof(double))) { fclose(f); return -6; }
     int *ci = (int *)malloc((size_t)(h.listed ? h.listed : 1) * sizeof(int));
     int *cj = (int *)malloc((size_t)(h.listed ? h.listed : 1) * sizeof(int));
     double *cv = (double *)malloc((size_t)(h.listed ? h.listed : 1) * sizeof(double));

@@ -158,3 +158,57 @@ def test_symmetric_file_must_be_square(tmp_path):
         f.write("%%MatrixMarket matrix coordinate real symmetric\n3 9 2\n1 8 1.5\n3 9 2.5\n")
     with pytest.raises(IOError, match="-7"):
         sb.mtx_read_csr(path)
+
+
+def test_entry_count_that_wraps_size_t_is_refused(tmp_path):
+    """Untrusted size line: 2^62 announced entries make `count * 4` wrap to 0 bytes; the loader must refuse (-6, out of
+    memory) instead of allocating a short buffer and writing the file's entries past it."""
+    import ctypes as C
+    path = str(tmp_path / "huge_count.mtx")
+    with open(path, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n4 4 4611686018427387904\n")
+        for k in range(64):
+            f.write("%d %d 1.0\n" % (k % 4 + 1, (k * 3) % 4 + 1))
+    rp = np.zeros(5, np.int64)
+    col = np.zeros(64, np.int32)
+    val = np.zeros(64)
+    rc = sb.lib().sblas_mtx_read_csr(path.encode(), rp.ctypes.data, col.ctypes.data, val.ctypes.data)
+    assert rc == -6, rc
+
+
+def test_mutated_files_never_crash_the_loader(tmp_path):
+    """Byte-level mutations of a valid file (truncation, deleted / duplicated / garbled lines, negative and huge
+    indices): the loader either reads a matrix or returns an error code; sizes it reports are what it writes."""
+    rng = np.random.default_rng(2024)
+    base = ["%%MatrixMarket matrix coordinate real symmetric", "% comment", "6 6 7",
+            "1 1 2.0", "2 1 -1.0", "3 3 4.5", "5 2 1e-3", "6 6 7", "4 4 1", "6 1 3.25"]
+    path = str(tmp_path / "mut.mtx")
+    outcomes = {"ok": 0, "err": 0}
+    for trial in range(300):
+        lines = list(base)
+        for _ in range(int(rng.integers(1, 4))):
+            k = int(rng.integers(0, len(lines)))
+            op = int(rng.integers(0, 6))
+            if op == 0 and len(lines) > 1:
+                del lines[k]
+            elif op == 1:
+                lines.insert(k, lines[k])
+            elif op == 2:
+                lines[k] = lines[k][: int(rng.integers(0, len(lines[k]) + 1))]
+            elif op == 3:
+                lines[k] = lines[k].replace("1", "-1", 1)
+            elif op == 4:
+                lines[k] = lines[k].replace("6", "999999999", 1)
+            else:
+                lines[k] = "".join(chr(int(c)) for c in rng.integers(32, 127, size=12))
+        with open(path, "w") as f:
+            f.write("\n".join(lines) + ("\n" if trial % 2 else ""))
+        try:
+            m, n, rp, col, val, sym = sb.mtx_read_csr(path)
+        except IOError:
+            outcomes["err"] += 1
+            continue
+        outcomes["ok"] += 1
+        assert rp[0] == 0 and (np.diff(rp) >= 0).all() and rp[-1] == len(col) == len(val)
+        assert len(col) == 0 or (col.min() >= 0 and col.max() < n)
+    assert outcomes["ok"] > 0 and outcomes["err"] > 0, outcomes
