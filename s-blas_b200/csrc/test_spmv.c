@@ -131,23 +131,44 @@ int main(int argc, char *argv[])
         }
         nnz = nnz_int;
         printf("m: %d n: %d nnz: %lld\n", m, n, nnz);
+        if (m <= 0 || n <= 0 || nnz < 0) {
+            printf("Error: the size line must hold a positive row and column count and a non-negative entry count.\n");
+            exit(1);
+        }
         cooRowIndex = (int *)pinned((size_t)nnz * sizeof(int));
         cooColIndex = (int *)pinned((size_t)nnz * sizeof(int));
         cooVal = (double *)pinned((size_t)nnz * sizeof(double));
         const char data_type = argv[6][0];
+        long long nread = 0;
         for (int i = 0; i < nnz; i++) {
             if (data_type == 'b') {
                 if (fscanf(f, "%d %d\n", &cooRowIndex[i], &cooColIndex[i]) < 2) break;
                 cooVal[i] = 0.00001;
             } else if (data_type == 'f') {
                 if (fscanf(f, "%d %d %lg\n", &cooRowIndex[i], &cooColIndex[i], &cooVal[i]) < 3) break;
+            } else {
+                break;
             }
             cooRowIndex[i]--;
             cooColIndex[i]--;
             if (cooRowIndex[i] < 0 || cooColIndex[i] < 0)
                 printf("i = %d [%d, %d] = %g\n", i, cooRowIndex[i], cooColIndex[i], cooVal[i]);
+            nread++;
         }
         fclose(f);
+        /* The reference carries on with whatever it read (dspmv_test.cu:150-166) and then counts rows through the
+         * indices unchecked; the file is untrusted input, so a short entry list or an index outside the matrix
+         * stops here instead of writing past the row counters. */
+        if (nread < nnz) {
+            printf("Error: the file holds %lld of the %lld entries its size line announces.\n", nread, nnz);
+            exit(1);
+        }
+        for (long long i = 0; i < nnz; i++)
+            if (cooRowIndex[i] < 0 || cooRowIndex[i] >= m || cooColIndex[i] < 0 || cooColIndex[i] >= n) {
+                printf("Error: entry %lld [%d, %d] lies outside the %d x %d matrix.\n", i, cooRowIndex[i] + 1,
+                       cooColIndex[i] + 1, m, n);
+                exit(1);
+            }
     } else if (input_type == 'g') {
         n = atoi(filename);
         m = n;
