@@ -93,4 +93,9 @@ int sblas_spmv_plan_create_flags(sblas_spmv_plan **plan, int version, int m, int
                                  const double *csrVal, const long long *csrRowPtr, const int *csrColIndex,
                                  int ngpu, int kernel, long long nb, int q, int flags);
 void sblas_pool_release(void);
+
+/* host arithmetic of the in-process x upload (sblas_plan.c), exposed for the CPU tests */
+void sblas_x_slice(long long n, int li, int live, long long *lo, long long *hi);
+void sblas_x_pull_range(long long slice_lo, long long slice_hi, long long win_lo, long long win_hi,
+                        long long *lo, long long *hi);
 #endif

@@ -996,6 +996,22 @@ fail:
  * the plan's streams.  In-process multi-GPU: every GPU uploads its 1/nd slice of x over its
  * own PCIe link and the slices are exchanged over NVLink (replaces nd full-size H2D copies,
  * dspmv_mgpu_v1.cu:183). */
+/* The part [*lo, *hi) of a peer's slice [slice_lo, slice_hi) of x that a GPU whose shard reads the columns
+ * [win_lo, win_hi] has to pull (empty when *hi <= *lo).  Pure host arithmetic, tested on the CPU. */
+void sblas_x_pull_range(long long slice_lo, long long slice_hi, long long win_lo, long long win_hi,
+                        long long *lo, long long *hi)
+{
+    *lo = slice_lo > win_lo ? slice_lo : win_lo;
+    *hi = slice_hi < win_hi + 1 ? slice_hi : win_hi + 1;
+}
+
+/* slice of x GPU number li of `live` uploads over its own PCIe link: [n*li/live, n*(li+1)/live) */
+void sblas_x_slice(long long n, int li, int live, long long *lo, long long *hi)
+{
+    *lo = n * li / live;
+    *hi = n * (li + 1) / live;
+}
+
 int sblas_spmv_plan_upload(sblas_spmv_plan *P, const double *x, const double *y)
 {
     int rc = 0;
@@ -1008,7 +1024,8 @@ int sblas_spmv_plan_upload(sblas_spmv_plan *P, const double *x, const double *y)
         if (D->seg_begin < 0) continue;
         CU(cudaSetDevice(D->device));
         cudaStream_t st = D->streams[0];
-        long long lo = (long long)P->n * li / live, hi = (long long)P->n * (li + 1) / live;
+        long long lo, hi;
+        sblas_x_slice(P->n, li, live, &lo, &hi);
         if (live == 1) { lo = D->col_lo; hi = (long long)D->col_hi + 1; }     /* only what the shard reads */
         D->xs_lo = lo; D->xs_hi = hi;
         if (x && live > 1)              /* peers may still be pulling the previous x out of this replica */
@@ -1031,8 +1048,8 @@ int sblas_spmv_plan_upload(sblas_spmv_plan *P, const double *x, const double *y)
                 if (o == d || O->seg_begin < 0 || O->xs_hi <= O->xs_lo) continue;
                 /* pull O's slice once it has landed there -- only the part inside the window of columns D's
                  * shard reads (a banded matrix on 8 GPUs needs about an eighth of x per GPU) */
-                const long long lo = O->xs_lo > D->col_lo ? O->xs_lo : D->col_lo;
-                const long long hi = O->xs_hi < (long long)D->col_hi + 1 ? O->xs_hi : (long long)D->col_hi + 1;
+                long long lo, hi;
+                sblas_x_pull_range(O->xs_lo, O->xs_hi, D->col_lo, D->col_hi, &lo, &hi);
                 if (hi <= lo) continue;
                 CU(cudaStreamWaitEvent(D->streams[0], O->ev_in, 0));
                 CU(cudaMemcpyPeerAsync(D->d_x + lo, D->device, O->d_x + lo, O->device,

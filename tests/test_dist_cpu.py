@@ -110,3 +110,45 @@ def test_rank_sharded_spmv_over_gloo(world, version, nb, q):
     mp.spawn(_worker, args=(world, _free_port(), version, nb, q, result_q), nprocs=world, join=True)
     worst = result_q.get()
     assert worst <= 1e-12, worst
+
+
+def test_in_process_x_upload_covers_every_window():
+    """Host arithmetic of the in-process multi-GPU upload (sblas_plan.c: sblas_spmv_plan_upload): GPU li of `live`
+    uploads slice li of x over its own PCIe link, then pulls from every peer only the part of the peer's slice that
+    lies inside the window of columns its own shard reads.  Whatever the windows are, every column of a GPU's window
+    must end up in its replica exactly once, and nothing outside the window may be pulled."""
+    import ctypes as C
+    import sblas_b200 as sb
+    L = sb.lib()
+    LL = C.c_longlong
+    L.sblas_x_slice.argtypes = [LL, C.c_int, C.c_int, C.POINTER(LL), C.POINTER(LL)]
+    L.sblas_x_slice.restype = None
+    L.sblas_x_pull_range.argtypes = [LL, LL, LL, LL, C.POINTER(LL), C.POINTER(LL)]
+    L.sblas_x_pull_range.restype = None
+    rng = np.random.default_rng(12)
+    for trial in range(200):
+        n = int(rng.integers(1, 5000)) if trial % 4 else int(rng.integers(1, 9))
+        live = int(rng.integers(2, 9))
+        slices = []
+        for li in range(live):
+            a, b = LL(), LL()
+            L.sblas_x_slice(n, li, live, C.byref(a), C.byref(b))
+            slices.append((a.value, b.value))
+        assert slices[0][0] == 0 and slices[-1][1] == n and all(slices[i][1] == slices[i + 1][0] for i in range(live - 1))
+        for d in range(live):
+            w = np.sort(rng.integers(0, n, size=2))
+            if trial % 7 == 0:
+                w = np.array([0, n - 1])                     # SBLAS_X_WINDOW=0: all of x
+            cover = np.zeros(n, np.int32)
+            cover[slices[d][0]:slices[d][1]] += 1             # its own slice comes from the host
+            for o in range(live):
+                if o == d or slices[o][1] <= slices[o][0]:
+                    continue
+                a, b = LL(), LL()
+                L.sblas_x_pull_range(slices[o][0], slices[o][1], int(w[0]), int(w[1]), C.byref(a), C.byref(b))
+                if b.value > a.value:
+                    assert slices[o][0] <= a.value and b.value <= slices[o][1]
+                    assert w[0] <= a.value and b.value <= w[1] + 1
+                    cover[a.value:b.value] += 1
+            assert (cover[w[0]:w[1] + 1] == 1).all(), (n, live, d, w.tolist())
+            assert (cover <= 1).all()
