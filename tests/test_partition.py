@@ -174,3 +174,42 @@ def test_partitions_bit_exact_on_the_full_size_row_pointers():
             for i in range(8):
                 for idx in (int(p8["start_idx"][i]), int(p8["end_idx"][i])):
                     assert ref(len(rp) - 1, rp, idx) == sb.get_row_from_index(len(rp) - 1, rp, idx), (name, idx)
+
+
+def test_partitioners_bit_exact_on_arbitrary_row_pointers_incl_empty_rows():
+    """Property test (hypothesis): row pointers with EMPTY rows (where the reference's bisection names a neighbouring
+    row), single-entry matrices, one huge row, more GPUs than entries.  The product's partitioners must
+    equal the oracle's field for field, and the oracle's row lookup is pinned on the reference's compiled helper."""
+    from hypothesis import given, settings, strategies as st
+
+    ref = oracle.ref_helper()
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.one_of(st.just(0), st.integers(0, 6), st.integers(0, 400)), min_size=1, max_size=60),
+           st.integers(1, 9), st.integers(1, 8))
+    def check(lens, ngpu, c):
+        rp = np.zeros(len(lens) + 1, np.int64)
+        rp[1:] = np.cumsum(lens)
+        m, nnz = len(lens), int(rp[-1])
+        for idx in {0, nnz // 2, max(nnz - 1, 0)}:
+            got = sb.get_row_from_index(m, rp, idx)
+            assert got == oracle.get_row_from_index(rp, idx)
+            if ref is not None:
+                assert got == ref(m, rp, idx)
+        a, b = sb.partition_baseline(rp, ngpu), oracle.partition_baseline(rp, ngpu)
+        for k in ("start_row", "end_row", "dev_m", "dev_nnz"):
+            assert (a[k] == b[k]).all(), ("baseline", k)
+        if nnz >= ngpu:
+            a, b = sb.partition_v1(rp, ngpu), oracle.partition_v1(rp, ngpu)
+            for k in KEYS:
+                assert (a[k] == b[k]).all(), ("v1", k)
+            assert a["start_idx"][0] == 0 and a["end_idx"][-1] == nnz - 1
+            assert (a["start_idx"][1:] == a["end_idx"][:-1] + 1).all()
+        nb = nnz // (ngpu * c)
+        if nb > 0:
+            a, b = sb.generate_tasks_v2(rp, nb), oracle.generate_tasks_v2(rp, nb)
+            for k in KEYS:
+                assert (a[k] == b[k]).all(), ("v2", k)
+            assert int(a["dev_nnz"].sum()) == nnz
+
+    check()
