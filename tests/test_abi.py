@@ -61,3 +61,22 @@ def test_fails_loudly_without_gpu():
 def test_time_helper():
     t0 = sb.get_time()
     assert sb.get_time() >= t0 > 1.0e9
+
+
+def test_every_public_header_stands_alone_in_c_and_cxx(tmp_path):
+    """A maintainer includes one header at a time from C (gcc) or C++ (g++, as the reference's .cu files do): each
+    header of include/ must compile on its own in both languages, with warnings as errors, and twice in a row
+    (include guards).  sblas_device.h and spmm/spmv_kernel.h need the CUDA runtime types, so the toolkit's include
+    directory is on the path like in the reference's Makefiles."""
+    import glob
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    for h in sorted(glob.glob(os.path.join(inc, "*.h"))):
+        name = os.path.basename(h)
+        for compiler, ext, std in (("gcc", "c", "-std=gnu11"), ("g++", "cpp", "-std=c++14")):
+            src = str(tmp_path / ("inc_%s.%s" % (name.replace(".", "_"), ext)))
+            open(src, "w").write('#include "%s"\n#include "%s"\nint main(void) { return 0; }\n' % (name, name))
+            p = subprocess.run([compiler, std, "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", inc, "-I", cuda_inc, src],
+                               capture_output=True, text=True)
+            assert p.returncode == 0, (name, compiler, p.stderr[:2000])
