@@ -166,11 +166,19 @@ static cudaError_t slab_get(int device, size_t need, int pooled, char **out, siz
     return cudaMalloc((void **)out, need);
 }
 
+/* blocks above SBLAS_POOL_MAX_GB (default 32) are not retained: a caller that pushes one giant matrix through the
+ * one-shot entry point should get the memory back like the reference gives it back */
+static size_t pool_cap(void)
+{
+    const int gb = env_int("SBLAS_POOL_MAX_GB", 32);
+    return (size_t)(gb > 0 ? gb : 0) << 30;
+}
+
 /* the current device is `device` and nothing is in flight on the block */
 static void slab_put(int device, char *ptr, size_t bytes, int pooled)
 {
     if (!ptr) return;
-    if (pooled && device >= 0 && device < SBLAS_POOL_DEVS) {
+    if (pooled && device >= 0 && device < SBLAS_POOL_DEVS && bytes <= pool_cap()) {
         pthread_mutex_lock(&g_pool_mu);
         if (!g_pool[device].ptr || g_pool[device].bytes < bytes) {   /* keep the larger of the two */
             char *t = g_pool[device].ptr;
